@@ -1,0 +1,449 @@
+// wd_aux_kernels.cuh — the HBM-bound / integer kernels around the convolutions:
+//   preprocess (uint8 HWC -> resize/crop/normalize -> [F,224,224,4]), NCHW-float packer, 3x3/2 max-pool,
+//   fused head (avg-pool + FC + segment consensus + softmax + argmax/threshold), rep counter,
+//   a plain fp32 direct convolution used only by the FP32_VALIDATE mode, and layout converters for test taps.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace wd {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Px4;  // 4-channel pixel store
+template <>
+struct Px4<__nv_bfloat16> {
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, float a, float b, float c) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(c, 0.0f);
+        uint2 v;
+        v.x = *reinterpret_cast<const uint32_t*>(&lo);
+        v.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p) = v;
+    }
+};
+template <>
+struct Px4<float> {
+    static __device__ __forceinline__ void store(float* p, float a, float b, float c) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, 0.0f);
+    }
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+
+
+// 8 consecutive channels <-> 8 floats, as one 128-bit (bf16) or two 128-bit (fp32) accesses
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        f[2 * q] = __uint_as_float(w[q] << 16);
+        f[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+        w[q] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Preprocess — reference: workoutdetector/datasets/build.py:131-136 (build_test_transform(False)):
+//   ConvertImageDtype(float32) -> Resize(256) (short side, bilinear, align_corners=False, no antialias as in the
+//   pinned torchvision 0.13) -> CenterCrop(224) -> Normalize(mean, std).
+// One CTA per (output frame, output row). The two source rows the bilinear kernel needs are one contiguous
+// byte span of the uint8 frame; it is staged in shared memory with coalesced 128-bit loads, then 224 threads
+// blend from shared memory and write one 4-channel pixel each (8 B bf16 / 16 B fp32, coalesced).
+// src_index (nullable) maps output frame -> source frame; a negative entry is an all-zero raw frame, which is
+// what the reference appends to short tail windows (utils/inference_count.py:413-414).
+// ------------------------------------------------------------------------------------------------
+struct PreArgs {
+    const uint8_t* frames;     // [nsrc, H, W, 3]
+    const int32_t* src_index;  // [nout] or nullptr (identity)
+    size_t total_bytes;        // nsrc*H*W*3
+    int nout, H, W;
+    int rh, rw;     // resized size (short side 256)
+    int top, left;  // crop offsets in the resized image
+    float scale_y, scale_x;  // H/rh, W/rw  (torch area_pixel_compute_scale, align_corners=False)
+    float in_scale;          // 1/255 (uint8 semantics) or 1 (float-promotion quirk, inference_count.py:413)
+    float mean[3], stdv[3];
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(224) preprocess_u8_kernel(const PreArgs a, OutT* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t srow[];
+    const int oy = blockIdx.x;
+    const int f = blockIdx.y;
+    const int ox = threadIdx.x;
+    const int src = a.src_index ? a.src_index[f] : f;
+    OutT* o = out + (((size_t)f * 224 + oy) * 224 + ox) * 4;
+    if (src < 0) {  // zero raw frame: (0*in_scale - mean) / std
+        Px4<OutT>::store(o, -a.mean[0] / a.stdv[0], -a.mean[1] / a.stdv[1], -a.mean[2] / a.stdv[2]);
+        return;
+    }
+    // vertical source coordinate (torch upsample_bilinear2d, align_corners=False)
+    float sy = a.scale_y * ((float)(oy + a.top) + 0.5f) - 0.5f;
+    sy = sy < 0.0f ? 0.0f : sy;
+    const int y0 = min((int)sy, a.H - 1);
+    const int y1 = min(y0 + 1, a.H - 1);
+    const float ly = sy - (float)y0;
+
+    const size_t row_bytes = (size_t)a.W * 3;
+    const size_t span_begin = ((size_t)src * a.H + y0) * row_bytes;
+    const size_t span_end = ((size_t)src * a.H + y1 + 1) * row_bytes;  // exclusive
+    const size_t abegin = span_begin & ~(size_t)15;
+    const int shift = (int)(span_begin - abegin);
+    const int nvec = (int)((span_end - abegin + 15) >> 4);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const size_t g = abegin + (size_t)v * 16;
+        uint4 val;
+        if (g + 16 <= a.total_bytes) {
+            val = __ldg(reinterpret_cast<const uint4*>(a.frames + g));
+        } else {
+            uint8_t tmp[16];
+            for (int b = 0; b < 16; ++b) tmp[b] = (g + b < a.total_bytes) ? a.frames[g + b] : 0;
+            val = *reinterpret_cast<const uint4*>(tmp);
+        }
+        *reinterpret_cast<uint4*>(srow + (size_t)v * 16) = val;
+    }
+    __syncthreads();
+
+    float sx = a.scale_x * ((float)(ox + a.left) + 0.5f) - 0.5f;
+    sx = sx < 0.0f ? 0.0f : sx;
+    const int x0 = min((int)sx, a.W - 1);
+    const int x1 = min(x0 + 1, a.W - 1);
+    const float lx = sx - (float)x0;
+    const uint8_t* r0 = srow + shift;
+    const uint8_t* r1 = r0 + (size_t)(y1 - y0) * row_bytes;
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v00 = (float)r0[x0 * 3 + c] * a.in_scale;
+        const float v01 = (float)r0[x1 * 3 + c] * a.in_scale;
+        const float v10 = (float)r1[x0 * 3 + c] * a.in_scale;
+        const float v11 = (float)r1[x1 * 3 + c] * a.in_scale;
+        // same association as ATen's upsample_bilinear2d: w00*v00 + w01*v01 + w10*v10 + w11*v11 grouped by row
+        const float top = v00 * (1.0f - lx) + v01 * lx;
+        const float bot = v10 * (1.0f - lx) + v11 * lx;
+        const float v = top * (1.0f - ly) + bot * ly;
+        res[c] = (v - a.mean[c]) / a.stdv[c];
+    }
+    Px4<OutT>::store(o, res[0], res[1], res[2]);
+}
+
+// [F,3,H,W] float (already normalised, what the reference nn.Module takes: tsm.py:409) -> [F,H,W,4]
+template <typename OutT>
+__global__ void pack_nchw_f32_kernel(const float* __restrict__ in, OutT* __restrict__ out, int F, int HW) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)F * HW) return;
+    const size_t f = i / HW;
+    const size_t p = i % HW;
+    const float* b = in + f * 3 * HW + p;
+    Px4<OutT>::store(out + i * 4, b[0], b[HW], b[2 * (size_t)HW]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Max-pool 3x3 stride 2 pad 1 over T-inner activations [clips, H, W, 8, C] -> [clips, H/2, W/2, 8, C].
+// One thread = 8 channels (16 B bf16 / 32 B fp32) of one output row.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int clips, int Hin, int Win,
+                                    int C) {
+    const int Hout = Hin / 2, Wout = Win / 2;
+    const int cvec = C / 8;
+    const size_t total = (size_t)clips * Hout * Wout * 8 * cvec;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cv = (int)(i % cvec);
+    size_t m = i / cvec;
+    const int t = (int)(m & 7);
+    size_t p = m >> 3;
+    const int ow = (int)(p % Wout);
+    p /= Wout;
+    const int oh = (int)(p % Hout);
+    const int n = (int)(p / Hout);
+    float best[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) best[q] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+        const int ih = oh * 2 - 1 + r;
+        if ((unsigned)ih >= (unsigned)Hin) continue;
+        for (int s = 0; s < 3; ++s) {
+            const int iw = ow * 2 - 1 + s;
+            if ((unsigned)iw >= (unsigned)Win) continue;
+            const T* src = in + ((((size_t)n * Hin + ih) * Win + iw) * 8 + t) * C + cv * 8;
+            float v[8];
+            load8(src, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) best[q] = fmaxf(best[q], v[q]);
+        }
+    }
+    store8(out + m * C + cv * 8, best);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head — reference: workoutdetector/models/tsm.py:411-419 (avgpool -> fc per frame -> mean over segments),
+// utils/visualize.py:140-150 (softmax), utils/eval.py:159-164 (first-max argmax, threshold).
+// One CTA per clip. In T-inner layout the 49 pixels x 8 segments of a clip are 392 contiguous rows, and
+//   mean_t( Wfc * avgpool(x_t) + b ) == Wfc * mean_{t,pixel}(x) + b,
+// so the whole head is one reduction over 392 rows followed by a [classes x 2048] mat-vec with warp-shuffle
+// reductions and a single-warp softmax.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadThreads = 256;
+constexpr int kMaxClasses = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kHeadThreads)
+head_kernel(const T* __restrict__ feat,  // [clips, rows_per_clip, C]
+            const float* __restrict__ wfc,  // [classes, C]
+            const float* __restrict__ bfc,  // [classes]
+            int rows_per_clip, int C, int classes, float threshold, int apply_softmax,
+            float* __restrict__ logits,  // [clips, classes]
+            float* __restrict__ probs,   // nullable
+            int32_t* __restrict__ state  // nullable
+) {
+    extern __shared__ float sm[];  // C feature means, then classes logits
+    float* sfeat = sm;
+    float* slog = sm + C;
+    const int n = blockIdx.x;
+    const T* base = feat + (size_t)n * rows_per_clip * C;
+    const float inv = 1.0f / (float)rows_per_clip;
+    // phase 1: column means. thread owns channel groups of 8.
+    for (int c8 = threadIdx.x; c8 < C / 8; c8 += kHeadThreads) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < rows_per_clip; ++r) {
+            float v[8];
+            load8(base + (size_t)r * C + c8 * 8, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += v[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sfeat[c8 * 8 + q] = acc[q] * inv;
+    }
+    __syncthreads();
+    // phase 2: one warp per class (strided), shuffle-reduced dot product.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < classes; k += kHeadThreads / 32) {
+        const float* w = wfc + (size_t)k * C;
+        float acc = 0.0f;
+        for (int c = lane; c < C; c += 32) acc += sfeat[c] * __ldg(w + c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const float v = acc + __ldg(bfc + k);
+            slog[k] = v;
+            logits[(size_t)n * classes + k] = v;
+        }
+    }
+    __syncthreads();
+    // phase 3: warp 0 — softmax, first-max argmax, threshold.
+    if (warp == 0) {
+        float mx = -INFINITY;
+        int arg = 0x7fffffff;
+        for (int k = lane; k < classes; k += 32) {
+            const float v = slog[k];
+            if (v > mx) {  // strict: keeps the first index within a lane
+                mx = v;
+                arg = k;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (omx > mx || (omx == mx && oarg < arg)) {
+                mx = omx;
+                arg = oarg;
+            }
+        }
+        float sum = 0.0f;
+        for (int k = lane; k < classes; k += 32) sum += expf(slog[k] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float rs = 1.0f / sum;
+        if (probs) {
+            for (int k = lane; k < classes; k += 32) probs[(size_t)n * classes + k] = expf(slog[k] - mx) * rs;
+        }
+        if (state && lane == 0) {
+            const float top = apply_softmax ? rs /* exp(0) / sum */ : mx;
+            state[n] = (top >= threshold) ? arg : -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rep counter — reference: workoutdetector/utils/inference_count.py:114-165 (pred_to_count).
+// One warp per video: lanes fetch 32 states at a time (coalesced), then every lane replays the same scalar
+// state machine on values broadcast with shuffles; lane 0 writes. Integer-only, bit-exact by construction.
+//   states [V, Wmax] int32, lens [V]; counts [V]; reps [V, reps_stride]; reps_len [V] (= 2*count)
+// ------------------------------------------------------------------------------------------------
+__global__ void count_reps_kernel(const int32_t* __restrict__ states, const int32_t* __restrict__ lens, int V,
+                                  int Wmax, int step, int32_t* __restrict__ counts, int32_t* __restrict__ reps,
+                                  int reps_stride, int32_t* __restrict__ reps_len) {
+    const int v = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (v >= V) return;
+    const int32_t* row = states + (size_t)v * Wmax;
+    const int len = lens ? min(lens[v], Wmax) : Wmax;
+    int count = 0;
+    bool have_last = false;
+    int last = 0;
+    int start_idx = 0;                            // prev_state_start_idx
+    int start_val = len > 0 ? __ldg(row) : 0;     // preds[prev_state_start_idx]
+    int32_t* rrow = reps ? reps + (size_t)v * reps_stride : nullptr;
+    for (int b = 0; b < len; b += 32) {
+        const int mine = (b + lane < len) ? __ldg(row + b + lane) : -1;
+        const int lim = min(32, len - b);
+        for (int q = 0; q < lim; ++q) {
+            const int pred = __shfl_sync(0xffffffffu, mine, q);
+            const int idx = b + q;
+            if (pred == -1) continue;
+            if (have_last && last != pred) {
+                if ((pred & 1) == 1 && last == pred - 1) {
+                    if (lane == 0 && rrow && 2 * count + 1 < reps_stride) {
+                        rrow[2 * count] = start_idx * step;
+                        rrow[2 * count + 1] = idx * step;
+                    }
+                    ++count;
+                }
+            }
+            last = pred;
+            have_last = true;
+            if (pred != start_val) {
+                start_idx = idx;
+                start_val = pred;
+            }
+        }
+    }
+    if (lane == 0) {
+        counts[v] = count;
+        if (reps_len) reps_len[v] = 2 * count;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32_VALIDATE mode: direct convolution in plain fp32 FMAs, same T-inner layout and the same on-the-fly
+// TemporalShift indexing as the tcgen05 path, weights [K, Cout] (cout contiguous). Slow by design: it exists
+// so the 1e-4 fp32 parity bar can be checked without tensor-core rounding.
+// ------------------------------------------------------------------------------------------------
+struct ConvF32Args {
+    const float* in;
+    float* out;
+    const float* residual;
+    const float* w;     // [K, Cout]
+    const float* bias;  // [Cout]
+    int M, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, pad, fold, relu, stem;
+};
+
+__global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Args a) {
+    // block: 64 couts x 4 rows
+    const int co = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int m = blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (m >= a.M || co >= a.Cout) return;
+    const int t = m & 7;
+    int p = m >> 3;
+    const int ow = p % a.Wout;
+    p /= a.Wout;
+    const int oh = p % a.Hout;
+    const int n = p / a.Hout;
+    float acc = 0.0f;
+    if (a.stem) {
+        // input [F, Hin, Win, 4]; weights [(r*7+s)*3 + c, Cout]
+        const int f = n * 8 + t;
+        for (int r = 0; r < 7; ++r) {
+            const int ih = oh * 2 - 3 + r;
+            if ((unsigned)ih >= (unsigned)a.Hin) continue;
+            for (int s = 0; s < 7; ++s) {
+                const int iw = ow * 2 - 3 + s;
+                if ((unsigned)iw >= (unsigned)a.Win) continue;
+                const float* px = a.in + (((size_t)f * a.Hin + ih) * a.Win + iw) * 4;
+                const float* wp = a.w + (size_t)((r * 7 + s) * 3) * a.Cout + co;
+                acc = fmaf(px[0], wp[0], acc);
+                acc = fmaf(px[1], wp[a.Cout], acc);
+                acc = fmaf(px[2], wp[2 * (size_t)a.Cout], acc);
+            }
+        }
+    } else {
+        for (int r = 0; r < a.R; ++r) {
+            const int ih = oh * a.stride - a.pad + r;
+            if ((unsigned)ih >= (unsigned)a.Hin) continue;
+            for (int s = 0; s < a.S; ++s) {
+                const int iw = ow * a.stride - a.pad + s;
+                if ((unsigned)iw >= (unsigned)a.Win) continue;
+                const size_t pix = (((size_t)n * a.Hin + ih) * a.Win + iw) * 8;
+                const float* wp = a.w + (size_t)((r * a.S + s) * a.Cin) * a.Cout + co;
+                for (int c = 0; c < a.Cin; ++c) {
+                    int tt = t;
+                    if (a.fold) tt += (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
+                    if ((unsigned)tt >= 8u) continue;
+                    acc = fmaf(a.in[(pix + tt) * a.Cin + c], wp[(size_t)c * a.Cout], acc);
+                }
+            }
+        }
+    }
+    acc += a.bias[co];
+    if (a.residual) acc += a.residual[(size_t)m * a.Cout + co];
+    if (a.relu) acc = fmaxf(acc, 0.0f);
+    a.out[(size_t)m * a.Cout + co] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Test tap: T-inner [clips, H, W, 8, C] (bf16 or fp32) -> fp32 NCHW frames [clips*8, C, H, W], the layout the
+// reference module's forward hooks see.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void untile_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int clips, int H, int W,
+                                      int C) {
+    const size_t total = (size_t)clips * H * W * 8 * C;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    size_t m = i / C;
+    const int t = (int)(m & 7);
+    size_t p = m >> 3;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    out[((((size_t)n * 8 + t) * C + c) * H + h) * W + w] = to_f32(in[i]);
+}
+
+// frames [F, H, W, 4] -> fp32 NCHW [F, 3, H, W] (tap for the preprocess / packer output)
+template <typename T>
+__global__ void frames_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int F, int HW) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)F * HW) return;
+    const size_t f = i / HW, p = i % HW;
+    for (int c = 0; c < 3; ++c) out[(f * 3 + c) * HW + p] = to_f32(in[i * 4 + c]);
+}
+
+}  // namespace wd

@@ -1,0 +1,889 @@
+// wd_engine.cu — C ABI (include/wd_b200.h) + host-side engine: BN folding, weight packing, TMA descriptors,
+// the TSM-R50 op plan and the launches.  Kernels live in wd_conv_umma.cuh / wd_aux_kernels.cuh.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wd_b200.h"
+#include "wd_aux_kernels.cuh"
+#include "wd_conv_umma.cuh"
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define WD_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(WD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define WD_TRY(expr)            \
+    do {                        \
+        int _r = (expr);        \
+        if (_r != WD_OK) return _r; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// Driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p)
+            return fail(WD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *out = fn;
+    return WD_OK;
+}
+
+// bf16 tensor map, 128-byte swizzle. dims/strides innermost first; strides in bytes for dims 1..rank-1.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                   const uint32_t* box) {
+    EncodeTiledFn fn;
+    WD_TRY(get_encode_fn(&fn));
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides[i - 1];
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                    bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return WD_OK;
+}
+
+inline uint16_t f32_to_bf16_bits(float f) {  // round-to-nearest-even, as __float2bfloat16_rn
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Plan
+// ---------------------------------------------------------------------------------------------------
+enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_MAXPOOL = 2, OP_HEAD = 3 };
+
+struct ConvLayer {
+    std::string name;      // e.g. "layer1.0.conv1"
+    std::string w_key[2];  // candidate state_dict names for the conv weight
+    std::string bn_prefix; // state_dict prefix of the BatchNorm
+    int Cin = 0, Cout = 0, k = 1, stride = 1, pad = 0;
+    int Hin = 0, Win = 0, Hout = 0, Wout = 0;
+    int fold = 0, relu = 0;
+    bool stem = false;
+    // device data
+    void* w_packed = nullptr;   // bf16 [Cout, Kp] (BF16 mode) or fp32 [K, Cout] (FP32 mode)
+    float* bias = nullptr;      // [Cout]
+    int kblocks = 0;            // Kp / 64
+    int tile_n = 64;
+    int a_mode = wd::A_GATHER;
+    CUtensorMap wmap;
+    CUtensorMap amap;
+};
+
+struct Op {
+    int kind = OP_CONV;
+    int conv = -1;           // index into convs
+    int in_buf = -1;         // -1 = external frames
+    int out_buf = -1;
+    int res_buf = -1;        // residual buffer or -1
+    std::string name;
+    int C = 0, H = 0, W = 0;  // output dims per frame
+    double macs_per_clip = 0;
+};
+
+}  // namespace
+
+struct wd_engine {
+    wd_model_desc desc{};
+    bool weights_loaded = false;
+    int use_tma_a = 1;
+    int tile_n_max = 256;
+    std::vector<ConvLayer> convs;
+    std::vector<Op> ops;
+    void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t buf_elems = 0;  // elements per workspace buffer
+    size_t elem_size = 2;
+    float* fc_w = nullptr;  // [num_class, 2048]
+    float* fc_b = nullptr;
+    int tap_idx = -1;
+    float* tap_dst = nullptr;
+    int64_t tap_cap = 0;
+    int64_t launches = 0;
+    // host-call staging (wd_infer_u8_host)
+    cudaStream_t hstream[2] = {nullptr, nullptr};
+    cudaEvent_t hevent[2] = {nullptr, nullptr};
+    uint8_t* h_u8[2] = {nullptr, nullptr};
+    void* h_frames[2] = {nullptr, nullptr};
+    float* h_logits = nullptr;
+    float* h_probs = nullptr;
+    int32_t* h_state = nullptr;
+    size_t h_u8_cap = 0;
+    int h_chunk = 0;
+};
+
+namespace {
+
+int out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+// Builds the conv list and the op plan for TSM ResNet-50 (torchvision v1.5 bottlenecks: stride on the 3x3).
+int build_plan(wd_engine* e) {
+    const int blocks[4] = {3, 4, 6, 3};
+    const int planes[4] = {64, 128, 256, 512};
+    auto add_conv = [&](const std::string& name, const std::string& wkey, const std::string& wkey2,
+                        const std::string& bn, int Cin, int Cout, int k, int stride, int Hin, int fold,
+                        int relu) -> int {
+        ConvLayer c;
+        c.name = name;
+        c.w_key[0] = wkey;
+        c.w_key[1] = wkey2;
+        c.bn_prefix = bn;
+        c.Cin = Cin;
+        c.Cout = Cout;
+        c.k = k;
+        c.stride = stride;
+        c.pad = k / 2;
+        c.Hin = c.Win = Hin;
+        c.Hout = c.Wout = out_dim(Hin, k, stride, c.pad);
+        c.fold = fold;
+        c.relu = relu;
+        e->convs.push_back(c);
+        return (int)e->convs.size() - 1;
+    };
+    auto add_conv_op = [&](int ci, int in_buf, int out_buf, int res_buf) {
+        const ConvLayer& c = e->convs[ci];
+        Op o;
+        o.kind = c.stem ? OP_STEM : OP_CONV;
+        o.conv = ci;
+        o.in_buf = in_buf;
+        o.out_buf = out_buf;
+        o.res_buf = res_buf;
+        o.name = c.name;
+        o.C = c.Cout;
+        o.H = c.Hout;
+        o.W = c.Wout;
+        o.macs_per_clip = 8.0 * c.Hout * c.Wout * (double)c.Cout * c.Cin * c.k * c.k;
+        e->ops.push_back(o);
+    };
+
+    const int H0 = e->desc.height;
+    int ci = add_conv("conv1", "base_model.conv1.weight", "", "base_model.bn1", 3, 64, 7, 2, H0, 0, 1);
+    e->convs[ci].stem = true;
+    add_conv_op(ci, -1, 0, -1);
+    {
+        Op o;
+        o.kind = OP_MAXPOOL;
+        o.in_buf = 0;
+        o.out_buf = 1;
+        o.name = "maxpool";
+        o.C = 64;
+        o.H = o.W = e->convs[ci].Hout / 2;
+        e->ops.push_back(o);
+    }
+    int cur = 1;
+    int H = e->convs[ci].Hout / 2;
+    int inplanes = 64;
+    for (int L = 0; L < 4; ++L) {
+        for (int b = 0; b < blocks[L]; ++b) {
+            const int stride = (L > 0 && b == 0) ? 2 : 1;
+            const int width = planes[L];
+            const int outp = width * 4;
+            const std::string pre = "base_model.layer" + std::to_string(L + 1) + "." + std::to_string(b);
+            const std::string nm = "layer" + std::to_string(L + 1) + "." + std::to_string(b);
+            int fr[3], nf = 0;
+            for (int i = 0; i < 4; ++i)
+                if (i != cur) fr[nf++] = i;
+            const int fold = e->desc.is_shift ? inplanes / e->desc.shift_div : 0;
+            const int c1 = add_conv(nm + ".conv1", pre + ".conv1.net.weight", pre + ".conv1.weight", pre + ".bn1",
+                                    inplanes, width, 1, 1, H, fold, 1);
+            add_conv_op(c1, cur, fr[0], -1);
+            const int c2 = add_conv(nm + ".conv2", pre + ".conv2.weight", "", pre + ".bn2", width, width, 3, stride,
+                                    H, 0, 1);
+            add_conv_op(c2, fr[0], fr[1], -1);
+            const int Ho = e->convs[c2].Hout;
+            int idbuf = cur;
+            if (b == 0) {
+                const int cd = add_conv(nm + ".downsample", pre + ".downsample.0.weight", "", pre + ".downsample.1",
+                                        inplanes, outp, 1, stride, H, 0, 0);
+                add_conv_op(cd, cur, fr[2], -1);
+                idbuf = fr[2];
+            }
+            const int c3 =
+                add_conv(nm + ".conv3", pre + ".conv3.weight", "", pre + ".bn3", width, outp, 1, 1, Ho, 0, 1);
+            add_conv_op(c3, fr[1], fr[0], idbuf);  // conv1's buffer is free again
+            cur = fr[0];
+            H = Ho;
+            inplanes = outp;
+        }
+    }
+    {
+        Op o;
+        o.kind = OP_HEAD;
+        o.in_buf = cur;
+        o.name = "head";
+        o.C = e->desc.num_class;
+        o.H = o.W = 1;
+        o.macs_per_clip = 8.0 * 2048 * e->desc.num_class;
+        e->ops.push_back(o);
+    }
+    // workspace size: the largest activation (stem output)
+    size_t mx = 0;
+    for (const ConvLayer& c : e->convs)
+        mx = std::max(mx, (size_t)e->desc.max_clips * 8 * c.Hout * c.Wout * c.Cout);
+    e->buf_elems = mx;
+    return WD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Launch helpers
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int AMODE>
+int launch_conv_t(const CUtensorMap& wmap, const CUtensorMap& amap, const wd::ConvArgs& a, cudaStream_t st) {
+    using L = wd::ConvSmem<BN, STAGES>;
+    static bool configured = false;
+    auto kfn = wd::conv_umma_kernel<BN, STAGES, AMODE>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+        configured = true;
+    }
+    const int m_tiles = (a.M + wd::kTileM - 1) / wd::kTileM;
+    const unsigned grid = (unsigned)m_tiles * (unsigned)a.n_tiles;
+    kfn<<<grid, wd::kConvThreads, L::kDynamic, st>>>(wmap, amap, a);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
+    const int mode = c.a_mode;
+    switch (c.tile_n) {
+        case 64:
+            if (mode == wd::A_STEM) return launch_conv_t<64, 4, wd::A_STEM>(c.wmap, c.amap, a, st);
+            if (mode == wd::A_TMA) return launch_conv_t<64, 4, wd::A_TMA>(c.wmap, c.amap, a, st);
+            return launch_conv_t<64, 4, wd::A_GATHER>(c.wmap, c.amap, a, st);
+        case 128:
+            if (mode == wd::A_TMA) return launch_conv_t<128, 3, wd::A_TMA>(c.wmap, c.amap, a, st);
+            if (mode == wd::A_GATHER) return launch_conv_t<128, 3, wd::A_GATHER>(c.wmap, c.amap, a, st);
+            break;
+        case 256:
+            if (mode == wd::A_TMA) return launch_conv_t<256, 4, wd::A_TMA>(c.wmap, c.amap, a, st);
+            if (mode == wd::A_GATHER) return launch_conv_t<256, 4, wd::A_GATHER>(c.wmap, c.amap, a, st);
+            break;
+    }
+    return fail(WD_ERR_INVALID, "no conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
+}
+
+wd::ConvArgs conv_args(const ConvLayer& c, const void* in, void* out, const void* res, int clips) {
+    wd::ConvArgs a{};
+    a.in = static_cast<const __nv_bfloat16*>(in);
+    a.out = static_cast<__nv_bfloat16*>(out);
+    a.residual = static_cast<const __nv_bfloat16*>(res);
+    a.bias = c.bias;
+    a.M = clips * c.Hout * c.Wout * 8;
+    a.Hin = c.Hin;
+    a.Win = c.Win;
+    a.Cin = c.Cin;
+    a.Hout = c.Hout;
+    a.Wout = c.Wout;
+    a.Cout = c.Cout;
+    a.R = a.S = c.k;
+    a.stride = c.stride;
+    a.pad = c.pad;
+    a.kblocks = c.kblocks;
+    a.cin_blocks = c.stem ? 1 : c.Cin / 64;
+    a.fold = c.fold;
+    a.relu = c.relu;
+    a.n_tiles = c.Cout / c.tile_n;
+    return a;
+}
+
+// Fold BN into (w, bias) on the host and upload in the layout of the engine's mode.
+//   w: [Cout, Cin, k, k] fp32; scale/shift: [Cout]
+int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const float* w, const float* scale,
+                const float* shift) {
+    const int K = c.Cin * c.k * c.k;
+    if (c.w_packed) cudaFree(c.w_packed);
+    if (c.bias) cudaFree(c.bias);
+    c.w_packed = nullptr;
+    c.bias = nullptr;
+    WD_CUDA(cudaMalloc(&c.bias, c.Cout * sizeof(float)));
+    WD_CUDA(cudaMemcpy(c.bias, shift, c.Cout * sizeof(float), cudaMemcpyHostToDevice));
+    if (mode == WD_MODE_FP32_VALIDATE) {
+        std::vector<float> p((size_t)K * c.Cout);
+        for (int co = 0; co < c.Cout; ++co)
+            for (int ci = 0; ci < c.Cin; ++ci)
+                for (int r = 0; r < c.k; ++r)
+                    for (int s = 0; s < c.k; ++s) {
+                        const float v = w[(((size_t)co * c.Cin + ci) * c.k + r) * c.k + s] * scale[co];
+                        p[(size_t)((r * c.k + s) * c.Cin + ci) * c.Cout + co] = v;
+                    }
+        WD_CUDA(cudaMalloc(&c.w_packed, p.size() * sizeof(float)));
+        WD_CUDA(cudaMemcpy(c.w_packed, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return WD_OK;
+    }
+    // BF16: [Cout, Kp], K-major
+    int Kp;
+    std::vector<uint16_t> p;
+    if (c.stem) {
+        // k-block kb, chunk j (8 elements = 2 pixels x 4 ch): r = 2*kb + (j>>2), s = 2*(j&3) + px - 1
+        Kp = 256;
+        p.assign((size_t)c.Cout * Kp, 0);
+        for (int co = 0; co < c.Cout; ++co)
+            for (int kb = 0; kb < 4; ++kb)
+                for (int j = 0; j < 8; ++j)
+                    for (int px = 0; px < 2; ++px)
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const int r = 2 * kb + (j >> 2);
+                            const int s = 2 * (j & 3) + px - 1;
+                            if (r >= 7 || s < 0 || s >= 7) continue;
+                            const float v = w[(((size_t)co * 3 + ch) * 7 + r) * 7 + s] * scale[co];
+                            p[(size_t)co * Kp + kb * 64 + j * 8 + px * 4 + ch] = f32_to_bf16_bits(v);
+                        }
+    } else {
+        if (c.Cin % 64 != 0) return fail(WD_ERR_INVALID, "%s: Cin=%d is not a multiple of 64", c.name.c_str(), c.Cin);
+        Kp = K;
+        p.resize((size_t)c.Cout * Kp);
+        for (int co = 0; co < c.Cout; ++co)
+            for (int ci = 0; ci < c.Cin; ++ci)
+                for (int r = 0; r < c.k; ++r)
+                    for (int s = 0; s < c.k; ++s) {
+                        const float v = w[(((size_t)co * c.Cin + ci) * c.k + r) * c.k + s] * scale[co];
+                        p[(size_t)co * Kp + (size_t)(r * c.k + s) * c.Cin + ci] = f32_to_bf16_bits(v);
+                    }
+    }
+    c.kblocks = Kp / 64;
+    c.tile_n = std::min(c.Cout, tile_n_max);
+    if (c.stem) c.tile_n = 64;
+    if (c.Cout % c.tile_n != 0)
+        return fail(WD_ERR_INVALID, "%s: Cout=%d not divisible by tile %d", c.name.c_str(), c.Cout, c.tile_n);
+    if (c.stem)
+        c.a_mode = wd::A_STEM;
+    else if (use_tma_a && c.k == 1 && c.stride == 1 && (c.fold == 0 || c.fold % 64 == 0))
+        c.a_mode = wd::A_TMA;
+    else
+        c.a_mode = wd::A_GATHER;
+    WD_CUDA(cudaMalloc(&c.w_packed, p.size() * 2));
+    WD_CUDA(cudaMemcpy(c.w_packed, p.data(), p.size() * 2, cudaMemcpyHostToDevice));
+    const uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)c.Cout};
+    const uint64_t strides[1] = {(uint64_t)Kp * 2};
+    const uint32_t box[2] = {64, (uint32_t)c.tile_n};
+    WD_TRY(make_tmap_bf16(&c.wmap, c.w_packed, 2, dims, strides, box));
+    return WD_OK;
+}
+
+// 3-D activation view {C, T=8, P} of a T-inner buffer for the A_TMA mode.
+int make_amap(CUtensorMap* map, const void* base, int Cin, size_t pixels) {
+    const uint64_t dims[3] = {(uint64_t)Cin, 8, (uint64_t)pixels};
+    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16};
+    const uint32_t box[3] = {64, 8, 16};
+    return make_tmap_bf16(map, base, 3, dims, strides, box);
+}
+
+int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, float* probs, int32_t* state,
+                float threshold, int apply_softmax, cudaStream_t st, float* op_ms) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (!e->weights_loaded) return fail(WD_ERR_STATE, "wd_forward called before wd_engine_load_weights");
+    if (n_clips < 0 || n_clips > e->desc.max_clips)
+        return fail(WD_ERR_INVALID, "n_clips=%d outside [0, max_clips=%d]", n_clips, e->desc.max_clips);
+    if (n_clips == 0) return WD_OK;
+    if (!frames || !logits) return fail(WD_ERR_INVALID, "frames/logits must not be NULL");
+    const bool f32 = e->desc.mode == WD_MODE_FP32_VALIDATE;
+    std::vector<cudaEvent_t> ev;
+    if (op_ms) {
+        ev.resize(e->ops.size() + 1);
+        for (auto& x : ev) WD_CUDA(cudaEventCreate(&x));
+        WD_CUDA(cudaEventRecord(ev[0], st));
+    }
+    for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+        const Op& o = e->ops[oi];
+        const void* in = o.in_buf < 0 ? frames : e->buf[o.in_buf];
+        void* out = o.out_buf < 0 ? nullptr : e->buf[o.out_buf];
+        const void* res = o.res_buf < 0 ? nullptr : e->buf[o.res_buf];
+        if (o.kind == OP_STEM || o.kind == OP_CONV) {
+            const ConvLayer& c = e->convs[o.conv];
+            if (f32) {
+                wd::ConvF32Args a{};
+                a.in = static_cast<const float*>(in);
+                a.out = static_cast<float*>(out);
+                a.residual = static_cast<const float*>(res);
+                a.w = static_cast<const float*>(c.w_packed);
+                a.bias = c.bias;
+                a.M = n_clips * c.Hout * c.Wout * 8;
+                a.Hin = c.Hin; a.Win = c.Win; a.Cin = c.Cin;
+                a.Hout = c.Hout; a.Wout = c.Wout; a.Cout = c.Cout;
+                a.R = a.S = c.k; a.stride = c.stride; a.pad = c.pad;
+                a.fold = c.fold; a.relu = c.relu; a.stem = c.stem ? 1 : 0;
+                dim3 grid((a.M + 3) / 4, (c.Cout + 63) / 64);
+                wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
+                WD_CUDA(cudaGetLastError());
+            } else {
+                wd::ConvArgs a = conv_args(c, in, out, res, n_clips);
+                WD_TRY(launch_conv(c, a, st));
+            }
+            ++e->launches;
+        } else if (o.kind == OP_MAXPOOL) {
+            const int Hin = o.H * 2;
+            const size_t total = (size_t)n_clips * o.H * o.W * 8 * (o.C / 8);
+            const unsigned grid = (unsigned)((total + 255) / 256);
+            if (f32)
+                wd::maxpool3x3s2_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in),
+                                                                      static_cast<float*>(out), n_clips, Hin, Hin, o.C);
+            else
+                wd::maxpool3x3s2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+                    static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n_clips, Hin, Hin, o.C);
+            WD_CUDA(cudaGetLastError());
+            ++e->launches;
+        } else {  // head
+            const ConvLayer& last = e->convs.back();
+            const int rows = last.Hout * last.Wout * 8;
+            const int C = last.Cout;
+            const size_t smem = (size_t)(C + e->desc.num_class) * sizeof(float);
+            if (f32)
+                wd::head_kernel<float><<<n_clips, wd::kHeadThreads, smem, st>>>(
+                    static_cast<const float*>(in), e->fc_w, e->fc_b, rows, C, e->desc.num_class, threshold,
+                    apply_softmax, logits, probs, state);
+            else
+                wd::head_kernel<__nv_bfloat16><<<n_clips, wd::kHeadThreads, smem, st>>>(
+                    static_cast<const __nv_bfloat16*>(in), e->fc_w, e->fc_b, rows, C, e->desc.num_class, threshold,
+                    apply_softmax, logits, probs, state);
+            WD_CUDA(cudaGetLastError());
+            ++e->launches;
+        }
+        if ((int)oi == e->tap_idx && e->tap_dst && o.kind != OP_HEAD) {
+            const size_t total = (size_t)n_clips * 8 * o.C * o.H * o.W;
+            if ((int64_t)total > e->tap_cap)
+                return fail(WD_ERR_INVALID, "tap buffer too small: need %zu elements, have %lld", total,
+                            (long long)e->tap_cap);
+            const unsigned grid = (unsigned)((total + 255) / 256);
+            if (f32)
+                wd::untile_to_nchw_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(out), e->tap_dst,
+                                                                        n_clips, o.H, o.W, o.C);
+            else
+                wd::untile_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+                    static_cast<const __nv_bfloat16*>(out), e->tap_dst, n_clips, o.H, o.W, o.C);
+            WD_CUDA(cudaGetLastError());
+        }
+        if (op_ms) WD_CUDA(cudaEventRecord(ev[oi + 1], st));
+    }
+    if (op_ms) {
+        WD_CUDA(cudaStreamSynchronize(st));
+        for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+            WD_CUDA(cudaEventElapsedTime(&op_ms[oi], ev[oi], ev[oi + 1]));
+        }
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
+    return WD_OK;
+}
+
+int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, const int32_t* src_index, int n_out,
+                    float in_scale, void* out, cudaStream_t st) {
+    if (n_out == 0) return WD_OK;
+    if (!frames || !out) return fail(WD_ERR_INVALID, "frames/out must not be NULL");
+    if (H < 2 || W < 2 || n_src < 1 || n_out < 0) return fail(WD_ERR_INVALID, "bad frame geometry %dx%d n=%d", H, W, n_src);
+    if (!src_index && n_out != n_src) return fail(WD_ERR_INVALID, "n_out must equal n_src without src_index");
+    wd::PreArgs a{};
+    a.frames = frames;
+    a.src_index = src_index;
+    a.total_bytes = (size_t)n_src * H * W * 3;
+    a.nout = n_out;
+    a.H = H;
+    a.W = W;
+    // torchvision Resize(256): short side -> 256, long side -> int(256 * long / short)
+    if (H <= W) {
+        a.rh = 256;
+        a.rw = (int)(256.0 * W / H);
+    } else {
+        a.rw = 256;
+        a.rh = (int)(256.0 * H / W);
+    }
+    // CenterCrop: int(round((size - 224) / 2.0)) — Python round() is half-to-even
+    a.top = (int)std::nearbyint((a.rh - 224) / 2.0);
+    a.left = (int)std::nearbyint((a.rw - 224) / 2.0);
+    a.scale_y = (float)H / (float)a.rh;
+    a.scale_x = (float)W / (float)a.rw;
+    a.in_scale = in_scale;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int i = 0; i < 3; ++i) {
+        a.mean[i] = mean[i];
+        a.stdv[i] = stdv[i];
+    }
+    const size_t smem = (size_t)2 * W * 3 + 48;
+    if (smem > 48 * 1024) return fail(WD_ERR_INVALID, "frame width %d too large for the row staging buffer", W);
+    dim3 grid(224, n_out);
+    if (mode == WD_MODE_FP32_VALIDATE)
+        wd::preprocess_u8_kernel<float><<<grid, 224, smem, st>>>(a, static_cast<float*>(out));
+    else
+        wd::preprocess_u8_kernel<__nv_bfloat16><<<grid, 224, smem, st>>>(a, static_cast<__nv_bfloat16*>(out));
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int wd_abi_version(void) { return WD_ABI_VERSION; }
+const char* wd_last_error(void) { return g_err; }
+
+int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
+    if (!d || !out) return fail(WD_ERR_INVALID, "desc/out must not be NULL");
+    *out = nullptr;
+    if (d->arch != WD_ARCH_TSM_R50) return fail(WD_ERR_INVALID, "unsupported arch %d", d->arch);
+    if (d->num_segments != 8) return fail(WD_ERR_INVALID, "num_segments must be 8 (got %d)", d->num_segments);
+    if (d->height != 224 || d->width != 224) return fail(WD_ERR_INVALID, "input must be 224x224");
+    if (d->num_class < 1 || d->num_class > wd::kMaxClasses) return fail(WD_ERR_INVALID, "bad num_class %d", d->num_class);
+    if (d->max_clips < 1) return fail(WD_ERR_INVALID, "max_clips must be >= 1");
+    if (d->is_shift && (d->shift_div < 1 || 64 % d->shift_div != 0 || (64 / d->shift_div) % 8 != 0))
+        return fail(WD_ERR_INVALID, "shift_div=%d: fold must be a multiple of 8 channels", d->shift_div);
+    if (d->mode != WD_MODE_BF16 && d->mode != WD_MODE_FP32_VALIDATE) return fail(WD_ERR_INVALID, "bad mode");
+    WD_CUDA(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    WD_CUDA(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10)
+        return fail(WD_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", d->device, prop.major,
+                    prop.minor);
+    wd_engine* e = new wd_engine();
+    e->desc = *d;
+    e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
+    int r = build_plan(e);
+    if (r != WD_OK) {
+        delete e;
+        return r;
+    }
+    for (int i = 0; i < 4; ++i) {
+        cudaError_t ce = cudaMalloc(&e->buf[i], e->buf_elems * e->elem_size);
+        if (ce != cudaSuccess) {
+            wd_engine_destroy(e);
+            return fail(WD_ERR_CUDA, "workspace cudaMalloc(%zu) failed: %s", e->buf_elems * e->elem_size,
+                        cudaGetErrorString(ce));
+        }
+    }
+    *out = e;
+    return WD_OK;
+}
+
+int wd_engine_destroy(wd_engine* e) {
+    if (!e) return WD_OK;
+    cudaSetDevice(e->desc.device);
+    for (auto& c : e->convs) {
+        if (c.w_packed) cudaFree(c.w_packed);
+        if (c.bias) cudaFree(c.bias);
+    }
+    for (int i = 0; i < 4; ++i)
+        if (e->buf[i]) cudaFree(e->buf[i]);
+    if (e->fc_w) cudaFree(e->fc_w);
+    if (e->fc_b) cudaFree(e->fc_b);
+    for (int i = 0; i < 2; ++i) {
+        if (e->h_u8[i]) cudaFree(e->h_u8[i]);
+        if (e->h_frames[i]) cudaFree(e->h_frames[i]);
+        if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
+        if (e->hevent[i]) cudaEventDestroy(e->hevent[i]);
+    }
+    if (e->h_logits) cudaFree(e->h_logits);
+    if (e->h_probs) cudaFree(e->h_probs);
+    if (e->h_state) cudaFree(e->h_state);
+    delete e;
+    return WD_OK;
+}
+
+int wd_engine_set_option(wd_engine* e, const char* key, int value) {
+    if (!e || !key) return fail(WD_ERR_INVALID, "engine/key NULL");
+    if (!strcmp(key, "use_tma_a")) {
+        e->use_tma_a = value ? 1 : 0;
+    } else if (!strcmp(key, "tile_n_max")) {
+        if (value != 64 && value != 128 && value != 256) return fail(WD_ERR_INVALID, "tile_n_max must be 64/128/256");
+        e->tile_n_max = value;
+    } else {
+        return fail(WD_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return WD_OK;
+}
+
+int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
+    if (!e || (!t && n > 0)) return fail(WD_ERR_INVALID, "engine/tensors NULL");
+    WD_CUDA(cudaSetDevice(e->desc.device));
+    std::map<std::string, const wd_named_tensor*> m;
+    for (int i = 0; i < n; ++i)
+        if (t[i].name && t[i].data) m[t[i].name] = &t[i];
+    auto find = [&](const std::string& k, int64_t numel, const float** out) -> int {
+        auto it = m.find(k);
+        if (it == m.end()) return fail(WD_ERR_MISSING, "state_dict tensor '%s' is missing", k.c_str());
+        if (it->second->numel != numel)
+            return fail(WD_ERR_INVALID, "tensor '%s' has %lld elements, expected %lld", k.c_str(),
+                        (long long)it->second->numel, (long long)numel);
+        *out = it->second->data;
+        return WD_OK;
+    };
+    for (ConvLayer& c : e->convs) {
+        const int64_t wn = (int64_t)c.Cout * c.Cin * c.k * c.k;
+        const float* w = nullptr;
+        std::string key = c.w_key[0];
+        if (m.find(key) == m.end() && !c.w_key[1].empty() && m.find(c.w_key[1]) != m.end()) key = c.w_key[1];
+        WD_TRY(find(key, wn, &w));
+        const float *g, *b, *mu, *var;
+        WD_TRY(find(c.bn_prefix + ".weight", c.Cout, &g));
+        WD_TRY(find(c.bn_prefix + ".bias", c.Cout, &b));
+        WD_TRY(find(c.bn_prefix + ".running_mean", c.Cout, &mu));
+        WD_TRY(find(c.bn_prefix + ".running_var", c.Cout, &var));
+        std::vector<float> scale(c.Cout), shift(c.Cout);
+        for (int i = 0; i < c.Cout; ++i) {
+            // torch BatchNorm2d eval: y = (x - mean) / sqrt(var + eps) * weight + bias, eps = 1e-5
+            const float s = g[i] / std::sqrt(var[i] + 1e-5f);
+            scale[i] = s;
+            shift[i] = b[i] - mu[i] * s;
+        }
+        WD_TRY(upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, w, scale.data(), shift.data()));
+    }
+    // A-operand TMA views over the workspace buffers
+    if (e->desc.mode == WD_MODE_BF16) {
+        for (const Op& o : e->ops) {
+            if (o.kind != OP_CONV) continue;
+            ConvLayer& c = e->convs[o.conv];
+            if (c.a_mode != wd::A_TMA) continue;
+            WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
+        }
+    }
+    const float *fw, *fb;
+    WD_TRY(find("fc.weight", (int64_t)e->desc.num_class * 2048, &fw));
+    WD_TRY(find("fc.bias", e->desc.num_class, &fb));
+    if (!e->fc_w) WD_CUDA(cudaMalloc(&e->fc_w, (size_t)e->desc.num_class * 2048 * sizeof(float)));
+    if (!e->fc_b) WD_CUDA(cudaMalloc(&e->fc_b, (size_t)e->desc.num_class * sizeof(float)));
+    WD_CUDA(cudaMemcpy(e->fc_w, fw, (size_t)e->desc.num_class * 2048 * sizeof(float), cudaMemcpyHostToDevice));
+    WD_CUDA(cudaMemcpy(e->fc_b, fb, (size_t)e->desc.num_class * sizeof(float), cudaMemcpyHostToDevice));
+    WD_CUDA(cudaDeviceSynchronize());
+    e->weights_loaded = true;
+    return WD_OK;
+}
+
+size_t wd_engine_frame_bytes(const wd_engine* e) { return e ? (size_t)224 * 224 * 4 * e->elem_size : 0; }
+
+int wd_preprocess_u8(wd_engine* e, const uint8_t* frames, int n_src, int H, int W, const int32_t* src_index,
+                     int n_out, float in_scale, void* out, void* stream) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    WD_TRY(preprocess_impl(e->desc.mode, frames, n_src, H, W, src_index, n_out, in_scale, out,
+                           static_cast<cudaStream_t>(stream)));
+    if (n_out > 0) ++e->launches;
+    return WD_OK;
+}
+
+int wd_pack_nchw_f32(wd_engine* e, const float* x, int n_frames, void* out, void* stream) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (n_frames == 0) return WD_OK;
+    if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
+    const int HW = 224 * 224;
+    const size_t total = (size_t)n_frames * HW;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->desc.mode == WD_MODE_FP32_VALIDATE)
+        wd::pack_nchw_f32_kernel<float><<<grid, 256, 0, st>>>(x, static_cast<float*>(out), n_frames, HW);
+    else
+        wd::pack_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), n_frames, HW);
+    WD_CUDA(cudaGetLastError());
+    ++e->launches;
+    return WD_OK;
+}
+
+int wd_forward(wd_engine* e, const void* frames, int n_clips, float* logits, float* probs, int32_t* state,
+               float threshold, int apply_softmax, void* stream) {
+    return run_forward(e, frames, n_clips, logits, probs, state, threshold, apply_softmax,
+                       static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int wd_forward_timed(wd_engine* e, const void* frames, int n_clips, float* logits, float* probs, int32_t* state,
+                     float threshold, int apply_softmax, void* stream, float* op_ms) {
+    if (!op_ms) return fail(WD_ERR_INVALID, "op_ms must not be NULL");
+    return run_forward(e, frames, n_clips, logits, probs, state, threshold, apply_softmax,
+                       static_cast<cudaStream_t>(stream), op_ms);
+}
+
+int wd_count_reps(const int32_t* states, const int32_t* lens, int V, int Wmax, int step, int32_t* counts,
+                  int32_t* reps, int reps_stride, int32_t* reps_len, void* stream) {
+    if (V < 0 || Wmax < 0) return fail(WD_ERR_INVALID, "negative V/Wmax");
+    if (V == 0) return WD_OK;
+    if (!counts || (Wmax > 0 && !states)) return fail(WD_ERR_INVALID, "states/counts must not be NULL");
+    const int threads = 128;  // 4 videos per block
+    const unsigned grid = (unsigned)(((size_t)V * 32 + threads - 1) / threads);
+    wd::count_reps_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(states, lens, V, Wmax, step, counts,
+                                                                                   reps, reps_stride, reps_len);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int W, float in_scale, float threshold,
+                     int apply_softmax, float* host_logits, float* host_probs, int32_t* host_state) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (!e->weights_loaded) return fail(WD_ERR_STATE, "weights not loaded");
+    if (n_clips == 0) return WD_OK;
+    if (!host || !host_logits) return fail(WD_ERR_INVALID, "host_frames/host_logits must not be NULL");
+    WD_CUDA(cudaSetDevice(e->desc.device));
+    const int chunk = std::min(e->desc.max_clips, 16);
+    const size_t clip_bytes = (size_t)8 * H * W * 3;
+    const int C = e->desc.num_class;
+    if (!e->hstream[0]) {
+        for (int i = 0; i < 2; ++i) {
+            WD_CUDA(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
+            WD_CUDA(cudaEventCreateWithFlags(&e->hevent[i], cudaEventDisableTiming));
+            WD_CUDA(cudaMalloc(&e->h_frames[i], (size_t)chunk * 8 * wd_engine_frame_bytes(e)));
+        }
+        WD_CUDA(cudaMalloc(&e->h_logits, (size_t)e->desc.max_clips * C * sizeof(float)));
+        WD_CUDA(cudaMalloc(&e->h_probs, (size_t)e->desc.max_clips * C * sizeof(float)));
+        WD_CUDA(cudaMalloc(&e->h_state, (size_t)e->desc.max_clips * sizeof(int32_t)));
+        e->h_chunk = chunk;
+    }
+    if (e->h_u8_cap < (size_t)chunk * clip_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (e->h_u8[i]) cudaFree(e->h_u8[i]);
+            e->h_u8[i] = nullptr;
+            WD_CUDA(cudaMalloc(&e->h_u8[i], (size_t)chunk * clip_bytes));
+        }
+        e->h_u8_cap = (size_t)chunk * clip_bytes;
+    }
+    // Copies run on hstream[slot]; compute for every chunk runs on hstream[0]-ordered stream `cs` because the
+    // workspace is shared. Slot reuse is fenced with events.
+    cudaStream_t cs = e->hstream[0];
+    cudaStream_t cp = e->hstream[1];
+    int done = 0, idx = 0;
+    while (done < n_clips) {
+        const int nc = std::min(chunk, n_clips - done);
+        const int slot = idx & 1;
+        // wait until the compute that last used this slot has finished before overwriting its staging buffer
+        if (idx >= 2) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
+        WD_CUDA(cudaMemcpyAsync(e->h_u8[slot], host + (size_t)done * clip_bytes, (size_t)nc * clip_bytes,
+                                cudaMemcpyHostToDevice, cp));
+        cudaEvent_t copied;
+        WD_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+        WD_CUDA(cudaEventRecord(copied, cp));
+        WD_CUDA(cudaStreamWaitEvent(cs, copied, 0));
+        WD_CUDA(cudaEventDestroy(copied));
+        WD_TRY(preprocess_impl(e->desc.mode, e->h_u8[slot], nc * 8, H, W, nullptr, nc * 8, in_scale,
+                               e->h_frames[slot], cs));
+        ++e->launches;
+        WD_TRY(run_forward(e, e->h_frames[slot], nc, e->h_logits + (size_t)done * C, e->h_probs + (size_t)done * C,
+                           e->h_state + done, threshold, apply_softmax, cs, nullptr));
+        WD_CUDA(cudaEventRecord(e->hevent[slot], cs));
+        done += nc;
+        ++idx;
+    }
+    WD_CUDA(cudaMemcpyAsync(host_logits, e->h_logits, (size_t)n_clips * C * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    if (host_probs)
+        WD_CUDA(cudaMemcpyAsync(host_probs, e->h_probs, (size_t)n_clips * C * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    if (host_state)
+        WD_CUDA(cudaMemcpyAsync(host_state, e->h_state, (size_t)n_clips * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    WD_CUDA(cudaStreamSynchronize(cs));
+    WD_CUDA(cudaStreamSynchronize(cp));
+    return WD_OK;
+}
+
+int wd_engine_num_ops(const wd_engine* e) { return e ? (int)e->ops.size() : 0; }
+
+int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int32_t* info, double* macs) {
+    if (!e || idx < 0 || idx >= (int)e->ops.size()) return fail(WD_ERR_INVALID, "op index %d out of range", idx);
+    const Op& o = e->ops[idx];
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", o.name.c_str());
+    if (info) {
+        for (int i = 0; i < 10; ++i) info[i] = 0;
+        info[0] = o.kind;
+        info[2] = o.C;
+        info[5] = o.H;
+        info[6] = o.W;
+        info[8] = -1;
+        if (o.conv >= 0) {
+            const ConvLayer& c = e->convs[o.conv];
+            info[1] = c.Cin;
+            info[3] = c.k;
+            info[4] = c.stride;
+            info[7] = c.fold;
+            info[8] = e->desc.mode == WD_MODE_BF16 ? c.a_mode : -1;
+            info[9] = c.tile_n;
+        }
+    }
+    if (macs) *macs = o.macs_per_clip;
+    return WD_OK;
+}
+
+int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t cap) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (idx >= (int)e->ops.size()) return fail(WD_ERR_INVALID, "tap index out of range");
+    e->tap_idx = idx;
+    e->tap_dst = dst;
+    e->tap_cap = cap;
+    return WD_OK;
+}
+
+int64_t wd_engine_launch_count(const wd_engine* e) { return e ? e->launches : 0; }
+
+int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
+                  int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
+                  int tile_n) {
+    if (!x || !w || !bias || !y) return fail(WD_ERR_INVALID, "NULL argument");
+    ConvLayer c;
+    c.name = "debug";
+    c.Cin = Cin;
+    c.Cout = Cout;
+    c.k = ksize;
+    c.stride = stride;
+    c.pad = ksize / 2;
+    c.Hin = Hin;
+    c.Win = Win;
+    c.Hout = out_dim(Hin, ksize, stride, c.pad);
+    c.Wout = out_dim(Win, ksize, stride, c.pad);
+    c.fold = fold;
+    c.relu = relu;
+    std::vector<float> ones(Cout, 1.0f);
+    WD_TRY(upload_conv(c, WD_MODE_BF16, tile_n, a_mode == wd::A_TMA ? 1 : 0, w, ones.data(), bias));
+    int rc = WD_OK;
+    if (a_mode == wd::A_TMA && c.a_mode != wd::A_TMA) {
+        rc = fail(WD_ERR_INVALID, "shape not eligible for the TMA A-operand path");
+    } else {
+        if (a_mode != wd::A_TMA) c.a_mode = wd::A_GATHER;
+        if (c.a_mode == wd::A_TMA) rc = make_amap(&c.amap, x, Cin, (size_t)clips * Hin * Win);
+        if (rc == WD_OK) {
+            wd::ConvArgs a = conv_args(c, x, y, residual, clips);
+            rc = launch_conv(c, a, nullptr);
+        }
+        if (rc == WD_OK) {
+            cudaError_t ce = cudaDeviceSynchronize();
+            if (ce != cudaSuccess) rc = fail(WD_ERR_CUDA, "debug conv failed: %s", cudaGetErrorString(ce));
+        }
+    }
+    cudaFree(c.w_packed);
+    cudaFree(c.bias);
+    return rc;
+}
+
+}  // extern "C"

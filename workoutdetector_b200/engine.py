@@ -1,0 +1,201 @@
+"""Thin Python face of the C-ABI engine. PyTorch is used for device memory and streams only."""
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MODE_BF16, MODE_FP32_VALIDATE, ModelDesc, NamedTensor, check
+
+OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head"}
+A_MODES = {0: "gather", 1: "stem", 2: "tma", -1: "-"}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One TSM-R50 inference engine bound to one GPU (wd_engine_create .. wd_engine_destroy)."""
+
+    def __init__(self, num_class: int, max_clips: int = 64, mode: str = "bf16", device: int = 0,
+                 is_shift: bool = True, shift_div: int = 8, num_segments: int = 8,
+                 use_tma_a: Optional[bool] = None, tile_n_max: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("workoutdetector_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.num_class = num_class
+        self.max_clips = max_clips
+        self.mode = {"bf16": MODE_BF16, "fp32": MODE_FP32_VALIDATE}[mode]
+        self.frame_dtype = torch.bfloat16 if self.mode == MODE_BF16 else torch.float32
+        desc = ModelDesc(arch=0, num_class=num_class, num_segments=num_segments, shift_div=shift_div,
+                         is_shift=int(bool(is_shift)), height=224, width=224, max_clips=max_clips, mode=self.mode,
+                         device=device)
+        h = C.c_void_p()
+        check(self.lib.wd_engine_create(C.byref(desc), C.byref(h)))
+        self.h = h
+        if use_tma_a is not None:
+            self.set_option("use_tma_a", int(use_tma_a))
+        if tile_n_max is not None:
+            self.set_option("tile_n_max", tile_n_max)
+        self._tap = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.wd_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration -------------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        check(self.lib.wd_engine_set_option(self.h, key.encode(), int(value)))
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """sd uses the reference parameter names (workoutdetector/models/tsm.py state_dict)."""
+        keep, arr = [], []
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            keep.append((k.encode(), t))
+        arr = (NamedTensor * len(keep))()
+        for i, (k, t) in enumerate(keep):
+            arr[i].name = k
+            arr[i].data = C.c_void_p(t.data_ptr())
+            arr[i].numel = t.numel()
+        check(self.lib.wd_engine_load_weights(self.h, arr, len(keep)))
+
+    # ---- ops ------------------------------------------------------------------------------------
+    def ops(self) -> List[dict]:
+        out = []
+        name = C.create_string_buffer(64)
+        info = (C.c_int32 * 10)()
+        macs = C.c_double()
+        for i in range(self.lib.wd_engine_num_ops(self.h)):
+            check(self.lib.wd_engine_op_info(self.h, i, name, 64, info, C.byref(macs)))
+            out.append(dict(index=i, name=name.value.decode(), kind=OP_KINDS[info[0]], cin=info[1], cout=info[2],
+                            k=info[3], stride=info[4], hout=info[5], wout=info[6], fold=info[7],
+                            a_mode=A_MODES[info[8]], tile_n=info[9], macs_per_clip=macs.value))
+        return out
+
+    def set_tap(self, idx: int, n_clips: int = 1) -> Optional[torch.Tensor]:
+        """Capture op idx's output as fp32 NCHW frames on the next forwards; idx < 0 disables."""
+        if idx < 0:
+            check(self.lib.wd_engine_set_tap(self.h, -1, None, 0))
+            self._tap = None
+            return None
+        o = self.ops()[idx]
+        t = torch.empty((n_clips * 8, o["cout"], o["hout"], o["wout"]), dtype=torch.float32, device=self.device)
+        check(self.lib.wd_engine_set_tap(self.h, idx, _ptr(t), t.numel()))
+        self._tap = t
+        return t
+
+    def preprocess_u8(self, frames: torch.Tensor, src_index: Optional[torch.Tensor] = None,
+                      in_scale: float = 1.0 / 255.0) -> torch.Tensor:
+        """frames: cuda uint8 [n,H,W,3] -> [n_out,224,224,4] (datasets/build.py:131-136 semantics)."""
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+        frames = frames.contiguous()
+        n, H, W, _ = frames.shape
+        if src_index is not None:
+            src_index = src_index.to(self.device, torch.int32).contiguous()
+            n_out = src_index.numel()
+            if n_out and int(src_index.max()) >= n:
+                raise IndexError("src_index entry beyond the last frame")
+        else:
+            n_out = n
+        out = torch.empty((n_out, 224, 224, 4), dtype=self.frame_dtype, device=self.device)
+        check(self.lib.wd_preprocess_u8(self.h, _ptr(frames), n, H, W, _ptr(src_index), n_out, float(in_scale),
+                                        _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def pack_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """x: cuda fp32 [F,3,224,224] normalised (what the reference module takes) -> engine frames."""
+        assert x.is_cuda and x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224)
+        x = x.to(torch.float32).contiguous()
+        out = torch.empty((x.shape[0], 224, 224, 4), dtype=self.frame_dtype, device=self.device)
+        check(self.lib.wd_pack_nchw_f32(self.h, _ptr(x), x.shape[0], _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def forward(self, frames: torch.Tensor, threshold: float = 0.5, softmax: bool = True,
+                timed: bool = False):
+        """frames [n_clips*8,224,224,4] -> (logits [n,C] f32, probs [n,C] f32, state [n] i32[, op_ms])."""
+        assert frames.is_cuda and frames.dtype == self.frame_dtype and frames.is_contiguous()
+        assert frames.shape[0] % 8 == 0 and tuple(frames.shape[1:]) == (224, 224, 4)
+        n = frames.shape[0] // 8
+        logits = torch.empty((n, self.num_class), dtype=torch.float32, device=self.device)
+        probs = torch.empty_like(logits)
+        state = torch.empty((n,), dtype=torch.int32, device=self.device)
+        if timed:
+            ms = (C.c_float * self.lib.wd_engine_num_ops(self.h))()
+            check(self.lib.wd_forward_timed(self.h, _ptr(frames), n, _ptr(logits), _ptr(probs), _ptr(state),
+                                            float(threshold), int(softmax), _stream_ptr(self.device), ms))
+            return logits, probs, state, list(ms)
+        check(self.lib.wd_forward(self.h, _ptr(frames), n, _ptr(logits), _ptr(probs), _ptr(state),
+                                  float(threshold), int(softmax), _stream_ptr(self.device)))
+        return logits, probs, state
+
+    def infer_u8_host(self, frames: torch.Tensor, in_scale: float = 1.0 / 255.0, threshold: float = 0.5,
+                      softmax: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """HOST uint8 [n_clips*8,H,W,3] -> HOST (logits, probs, state); copies happen inside the call."""
+        assert not frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous()
+        F, H, W, _ = frames.shape
+        assert F % 8 == 0
+        n = F // 8
+        logits = torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True)
+        probs = torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True)
+        state = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+        check(self.lib.wd_infer_u8_host(self.h, _ptr(frames), n, H, W, float(in_scale), float(threshold),
+                                        int(softmax), _ptr(logits), _ptr(probs), _ptr(state)))
+        return logits, probs, state
+
+    def launch_count(self) -> int:
+        return int(self.lib.wd_engine_launch_count(self.h))
+
+
+def count_reps(states: torch.Tensor, lens: Optional[torch.Tensor] = None, step: int = 8):
+    """Batched pred_to_count (utils/inference_count.py:114-165) on the GPU.
+
+    states: cuda int32 [V, W]; lens: cuda int32 [V] or None. Returns (counts [V], reps [V, W+1], reps_len [V]).
+    """
+    if not states.is_cuda:
+        raise RuntimeError("count_reps needs CUDA tensors; there is no CPU fallback")
+    lib = _lib.load()
+    states = states.to(torch.int32).contiguous()
+    V, W = states.shape
+    if lens is not None:
+        lens = lens.to(states.device, torch.int32).contiguous()
+    counts = torch.zeros((V,), dtype=torch.int32, device=states.device)
+    stride = W + 1
+    reps = torch.zeros((V, stride), dtype=torch.int32, device=states.device)
+    reps_len = torch.zeros((V,), dtype=torch.int32, device=states.device)
+    check(lib.wd_count_reps(_ptr(states), _ptr(lens), V, W, int(step), _ptr(counts), _ptr(reps), stride,
+                            _ptr(reps_len), _stream_ptr(states.device)))
+    return counts, reps, reps_len
+
+
+def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor], stride: int,
+               fold: int, relu: bool, a_mode: str, tile_n: int) -> torch.Tensor:
+    """Test hook: one tcgen05 conv. x bf16 cuda [clips,H,W,8,Cin] (T-inner); w fp32 [Cout,Cin,k,k]."""
+    lib = _lib.load()
+    clips, Hin, Win, T, Cin = x.shape
+    assert T == 8 and x.dtype == torch.bfloat16 and x.is_cuda and x.is_contiguous()
+    Cout, _, k, _ = w.shape
+    Hout = (Hin + 2 * (k // 2) - k) // stride + 1
+    Wout = (Win + 2 * (k // 2) - k) // stride + 1
+    y = torch.empty((clips, Hout, Wout, 8, Cout), dtype=torch.bfloat16, device=x.device)
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    bc = bias.detach().to("cpu", torch.float32).contiguous()
+    torch.cuda.synchronize()
+    check(lib.wd_debug_conv(_ptr(x), _ptr(wc), _ptr(bc), _ptr(residual), _ptr(y), clips, Hin, Win, Cin, Cout, k,
+                            stride, fold, int(relu), {"gather": 0, "tma": 2}[a_mode], tile_n))
+    return y
