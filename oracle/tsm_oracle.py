@@ -43,7 +43,7 @@ def reference_init_state_dict(num_class: int, seed: int, num_segments: int = 8) 
     torch.nn.init.constant_(fc.bias, 0)
     sd = OrderedDict()
     for k, v in net.state_dict().items():
-        if k.startswith("fc."):
+        if k.startswith("fc.") or k.endswith("num_batches_tracked"):
             continue
         parts = k.split(".")
         if len(parts) >= 3 and parts[0].startswith("layer") and parts[2] == "conv1":
