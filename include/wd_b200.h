@@ -114,6 +114,12 @@ int wd_forward_timed(wd_engine* e, const void* frames, int n_clips, float* logit
 int wd_count_reps(const int32_t* states, const int32_t* lens, int V, int Wmax, int step, int32_t* counts,
                   int32_t* reps, int reps_stride, int32_t* reps_len, void* stream);
 
+/* Replaces to_softmax (utils/visualize.py:140-150) + the arg-max / threshold loop of utils/eval.py:153-164 for
+ * score arrays that already exist (score JSONs): scores device fp32 [rows, classes] -> probs (nullable) and
+ * state int32 [rows] with the same rule as wd_forward. */
+int wd_scores_to_states(const float* scores, int rows, int classes, float threshold, int apply_softmax,
+                        float* probs, int32_t* state, void* stream);
+
 /* End-to-end convenience for host callers (what inference_video, utils/inference_count.py:246-282, does per
  * window, batched): pinned-or-pageable HOST uint8 clips [n_clips*8, H, W, 3] -> H2D -> preprocess -> forward ->
  * D2H of logits/probs/state into HOST arrays (any may be NULL except logits).  Chunks are double-buffered on two

@@ -301,6 +301,47 @@ head_kernel(const T* __restrict__ feat,  // [clips, rows_per_clip, C]
 }
 
 // ------------------------------------------------------------------------------------------------
+// Scores -> states for score arrays that already exist (the JSON route of utils/eval.py:153-164): one warp per
+// window row; softmax (optional), first-max arg-max, threshold. Same arithmetic as phase 3 of head_kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void scores_to_states_kernel(const float* __restrict__ scores, int rows, int classes, float threshold,
+                                        int apply_softmax, float* __restrict__ probs, int32_t* __restrict__ state) {
+    const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = scores + (size_t)row * classes;
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int k = lane; k < classes; k += 32) {
+        const float v = s[k];
+        if (v > mx) {
+            mx = v;
+            arg = k;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (omx > mx || (omx == mx && oarg < arg)) {
+            mx = omx;
+            arg = oarg;
+        }
+    }
+    float sum = 0.0f;
+    for (int k = lane; k < classes; k += 32) sum += expf(s[k] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float rs = 1.0f / sum;
+    if (probs)
+        for (int k = lane; k < classes; k += 32) probs[(size_t)row * classes + k] = expf(s[k] - mx) * rs;
+    if (state && lane == 0) {
+        const float top = apply_softmax ? rs : mx;
+        state[row] = (top >= threshold) ? arg : -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Rep counter — reference: workoutdetector/utils/inference_count.py:114-165 (pred_to_count).
 // One warp per video: lanes fetch 32 states at a time (coalesced), then every lane replays the same scalar
 // state machine on values broadcast with shuffles; lane 0 writes. Integer-only, bit-exact by construction.

@@ -744,6 +744,19 @@ int wd_count_reps(const int32_t* states, const int32_t* lens, int V, int Wmax, i
     return WD_OK;
 }
 
+int wd_scores_to_states(const float* scores, int rows, int classes, float threshold, int apply_softmax,
+                        float* probs, int32_t* state, void* stream) {
+    if (rows < 0 || classes < 1) return fail(WD_ERR_INVALID, "bad rows/classes");
+    if (rows == 0) return WD_OK;
+    if (!scores || !state) return fail(WD_ERR_INVALID, "scores/state must not be NULL");
+    const int threads = 128;
+    const unsigned grid = (unsigned)(((size_t)rows * 32 + threads - 1) / threads);
+    wd::scores_to_states_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        scores, rows, classes, threshold, apply_softmax, probs, state);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int W, float in_scale, float threshold,
                      int apply_softmax, float* host_logits, float* host_probs, int32_t* host_state) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");

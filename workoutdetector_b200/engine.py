@@ -183,6 +183,20 @@ def count_reps(states: torch.Tensor, lens: Optional[torch.Tensor] = None, step: 
     return counts, reps, reps_len
 
 
+def scores_to_states(scores: torch.Tensor, threshold: float = 0.5, softmax: bool = True):
+    """scores cuda fp32 [rows, C] -> (probs [rows, C], state int32 [rows]); utils/eval.py:153-164 on the GPU."""
+    if not scores.is_cuda:
+        raise RuntimeError("scores_to_states needs CUDA tensors; there is no CPU fallback")
+    lib = _lib.load()
+    scores = scores.to(torch.float32).contiguous()
+    rows, classes = scores.shape
+    probs = torch.empty_like(scores)
+    state = torch.empty((rows,), dtype=torch.int32, device=scores.device)
+    check(lib.wd_scores_to_states(_ptr(scores), rows, classes, float(threshold), int(softmax), _ptr(probs),
+                                  _ptr(state), _stream_ptr(scores.device)))
+    return probs, state
+
+
 def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor], stride: int,
                fold: int, relu: bool, a_mode: str, tile_n: int) -> torch.Tensor:
     """Test hook: one tcgen05 conv. x bf16 cuda [clips,H,W,8,Cin] (T-inner); w fp32 [Cout,Cin,k,k]."""

@@ -104,6 +104,7 @@ class TSM(nn.Module):
         net = _resnet(base_model)
         if is_shift:
             make_temporal_shift(net, num_segments, n_div=shift_div, place=shift_place)
+        self.base_model = net  # registered first so state_dict order matches the reference (tsm.py:268)
         self.input_size = 224
         self.input_mean = [0.485, 0.456, 0.406]
         self.input_std = [0.229, 0.224, 0.225]
