@@ -136,17 +136,17 @@ int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int
 /* After op `idx` runs in the next forwards, its output is converted to fp32 NCHW frames [n_clips*8, C, H, W]
  * at dst (device).  idx < 0 disables.  The head op (logits) cannot be tapped. */
 int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems);
-/* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256).  Takes effect at the next wd_engine_load_weights. */
+/* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (0/1: persistent vs one-tile-per-CTA kernel).  Takes effect at the next wd_engine_load_weights. */
 int wd_engine_set_option(wd_engine* e, const char* key, int value);
 /* Number of kernels the engine launched since creation (all are this library's own kernels). */
 int64_t wd_engine_launch_count(const wd_engine* e);
 
 /* Run ONE convolution outside an engine (tests): x device bf16 T-inner [clips,Hin,Win,8,Cin], w host fp32
  * [Cout,Cin,k,k], bias host fp32 [Cout], residual device bf16 or NULL -> y device bf16 [clips,Hout,Wout,8,Cout].
- * a_mode: 0 gather, 2 TMA (1x1 stride 1 only).  Synchronous. */
+ * a_mode: 0 gather, 2 TMA (1x1 stride 1 only); persistent selects the kernel variant.  Synchronous. */
 int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
                   int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
-                  int tile_n);
+                  int tile_n, int persistent);
 
 #ifdef __cplusplus
 }

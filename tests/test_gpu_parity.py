@@ -202,11 +202,14 @@ CONV_CASES = [
     (1, 7, 512, 2048, 1, 1, 0, 1, 1, "tma", 256),         # conv3 + residual + relu, 8 n-tiles, M tail
     (1, 7, 512, 512, 3, 1, 0, 1, 0, "gather", 256),
     (3, 7, 128, 512, 1, 1, 0, 1, 1, "gather", 128),
+    (40, 14, 256, 1024, 1, 1, 0, 1, 1, "tma", 256),       # 490 x 4 tiles: several tiles per persistent CTA
+    (24, 14, 128, 128, 3, 1, 0, 1, 0, "gather", 128),     # 294 tiles through the gather producers
 ]
 
 
+@pytest.mark.parametrize("persistent", [True, False], ids=["persistent", "tile_per_cta"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[f"c{i}" for i in range(len(CONV_CASES))])
-def test_conv_umma_vs_torch(case):
+def test_conv_umma_vs_torch(case, persistent):
     from workoutdetector_b200.engine import debug_conv
     torch.backends.cudnn.allow_tf32 = False
     clips, H, Cin, Cout, k, stride, fold, relu, res, mode, tile_n = case
@@ -216,7 +219,7 @@ def test_conv_umma_vs_torch(case):
     b = torch.randn(Cout, generator=g)
     Ho = (H + 2 * (k // 2) - k) // stride + 1
     r = torch.randn(clips, Ho, Ho, 8, Cout, generator=g).to(torch.bfloat16).cuda() if res else None
-    y = debug_conv(x, w, b, r, stride, fold, bool(relu), mode, tile_n).float()
+    y = debug_conv(x, w, b, r, stride, fold, bool(relu), mode, tile_n, persistent).float()
     xf = x.float().permute(0, 3, 4, 1, 2).reshape(clips * 8, Cin, H, H)
     if fold:
         xf = O.temporal_shift(xf.cpu(), 8, Cin // fold).cuda()

@@ -25,6 +25,9 @@ CASES = [
     ("1x1 residual relu tma 2 n-tiles", 1, 7, 512, 2048, 1, 1, 0, 1, 1, "tma", 256),
     ("1x1 residual relu gather tail", 1, 7, 128, 512, 1, 1, 0, 1, 1, "gather", 128),
     ("3x3 7x7 tail", 1, 7, 512, 512, 3, 1, 0, 1, 0, "gather", 256),
+    ("1x1 many tiles tma res", 40, 14, 256, 1024, 1, 1, 0, 1, 1, "tma", 256),
+    ("3x3 many tiles gather", 24, 14, 128, 128, 3, 1, 0, 1, 0, "gather", 128),
+    ("1x1 k64 n256 many tiles res", 16, 28, 64, 256, 1, 1, 0, 1, 1, "tma", 256),
 ]
 
 
@@ -41,7 +44,8 @@ def run_case(i):
     b = torch.randn(Cout, generator=g)
     Ho = (H + 2 * (k // 2) - k) // stride + 1
     r = torch.randn(clips, Ho, Ho, 8, Cout, generator=g).to(torch.bfloat16).cuda() if res else None
-    y = debug_conv(x, w, b, r, stride, fold, bool(relu), mode, tile_n)
+    persistent = os.environ.get('WD_PERSISTENT', '1') == '1'
+    y = debug_conv(x, w, b, r, stride, fold, bool(relu), mode, tile_n, persistent)
     # reference: frames NCHW fp32
     xf = x.float().permute(0, 3, 4, 1, 2).reshape(clips, 8, Cin, H, H)
     if fold:

@@ -116,11 +116,14 @@ def _engine_vs_oracle(mode, use_tma):
 
 
 def sec_perf():
+    import json
     import torch
     from workoutdetector_b200.engine import Engine
     sd = _weights()
-    for n_clips, tn in ((64, 256), (64, 128), (8, 256)):
-        eng = Engine(12, max_clips=n_clips, mode="bf16", tile_n_max=tn)
+    report = {}
+    configs = [(64, 256, 1), (64, 128, 1), (64, 256, 0), (8, 256, 1)]
+    for n_clips, tn, pers in configs:
+        eng = Engine(12, max_clips=n_clips, mode="bf16", tile_n_max=tn, persistent=bool(pers))
         eng.load_state_dict(sd)
         u8 = torch.randint(0, 256, (n_clips * 8, 224, 224, 3), dtype=torch.uint8, device="cuda")
         frames = eng.preprocess_u8(u8)
@@ -135,17 +138,29 @@ def sec_perf():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        print(f"forward n_clips={n_clips} tile_n_max={tn}: {ms:.3f} ms -> {n_clips / ms * 1e3:.0f} clips/s "
-              f"({n_clips / ms * 1e3 * 65.394e9 / 1e12:.0f} TFLOP/s)")
-        *_, op_ms = eng.forward(frames, timed=True)
+        print(f"forward n_clips={n_clips} tile_n_max={tn} persistent={pers}: {ms:.3f} ms -> "
+              f"{n_clips / ms * 1e3:.0f} clips/s ({n_clips / ms * 1e3 * 65.394e9 / 1e12:.0f} TFLOP/s)")
+        acc = None
+        for _ in range(3):
+            *_, op_ms = eng.forward(frames, timed=True)
+            acc = op_ms if acc is None else [a + b for a, b in zip(acc, op_ms)]
+        op_ms = [a / 3 for a in acc]
         ops = eng.ops()
-        rows = sorted(zip(op_ms, ops), key=lambda r: -r[0])
-        tot = sum(op_ms)
-        print(f"  timed sum {tot:.3f} ms; top ops:")
-        for m, o in rows[:14]:
+        rows = []
+        for m, o in zip(op_ms, ops):
             tf = 2 * o["macs_per_clip"] * n_clips / (m * 1e-3) / 1e12 if m > 0 else 0
-            print(f"    {o['name']:22s} {o['kind']:7s} a={o['a_mode']:6s} n={o['tile_n']:3d} {m:.3f} ms {tf:7.1f} TFLOP/s")
+            rows.append(dict(name=o["name"], kind=o["kind"], a_mode=o["a_mode"], tile_n=o["tile_n"], ms=m, tflops=tf,
+                             cin=o["cin"], cout=o["cout"], k=o["k"], hout=o["hout"]))
+        report[f"clips{n_clips}_tn{tn}_p{pers}"] = dict(ms=ms, clips_per_s=n_clips / ms * 1e3, ops=rows)
+        print(f"  timed sum {sum(op_ms):.3f} ms")
+        if (n_clips, tn) == (64, 256):
+            for r in rows:
+                print(f"    {r['name']:22s} {r['kind']:7s} a={r['a_mode']:6s} n={r['tile_n']:3d} {r['ms']:.3f} ms "
+                      f"{r['tflops']:7.1f} TFLOP/s")
         eng.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "perf_ops.json"), "w") as f:
+        json.dump(report, f, indent=1)
     return True
 
 

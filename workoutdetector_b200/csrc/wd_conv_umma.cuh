@@ -43,7 +43,8 @@ struct ConvArgs {
     int cin_blocks;  // Cin/64
     int fold;        // TemporalShift fold in channels (Cin/shift_div) or 0
     int relu;
-    int n_tiles;  // Cout / BN
+    int n_tiles;    // Cout / BN
+    int num_tiles;  // m_tiles * n_tiles (persistent kernel)
 };
 
 template <int BN, int STAGES>

@@ -15,6 +15,7 @@
 
 #include "../../include/wd_b200.h"
 #include "wd_aux_kernels.cuh"
+#include "wd_conv_persistent.cuh"
 #include "wd_conv_umma.cuh"
 
 namespace {
@@ -112,6 +113,8 @@ struct ConvLayer {
     int a_mode = wd::A_GATHER;
     CUtensorMap wmap;
     CUtensorMap amap;
+    CUtensorMap omap;  // output [rows, Cout], box {64, 32} (persistent kernel's TMA store)
+    CUtensorMap rmap;  // residual, same geometry
 };
 
 struct Op {
@@ -132,6 +135,8 @@ struct wd_engine {
     bool weights_loaded = false;
     int use_tma_a = 1;
     int tile_n_max = 256;
+    int persistent = 1;
+    int sm_count = 148;
     std::vector<ConvLayer> convs;
     std::vector<Op> ops;
     void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -286,6 +291,41 @@ int launch_conv_t(const CUtensorMap& wmap, const CUtensorMap& amap, const wd::Co
     return WD_OK;
 }
 
+template <int BN, int STAGES, int AMODE>
+int launch_persist_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using L = wd::PersistSmem<BN, STAGES>;
+    static bool configured = false;
+    auto kfn = wd::conv_umma_persistent<BN, STAGES, AMODE>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+        configured = true;
+    }
+    const unsigned grid = (unsigned)std::min(a.num_tiles, sm_count);
+    const unsigned threads = AMODE == wd::A_TMA ? 192 : 320;
+    kfn<<<grid, threads, L::kDynamic, st>>>(c.wmap, c.amap, c.omap, c.rmap, a);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int launch_persist(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    const int mode = c.a_mode;
+    switch (c.tile_n) {
+        case 64:
+            if (mode == wd::A_STEM) return launch_persist_t<64, 6, wd::A_STEM>(c, a, sm_count, st);
+            if (mode == wd::A_TMA) return launch_persist_t<64, 6, wd::A_TMA>(c, a, sm_count, st);
+            return launch_persist_t<64, 6, wd::A_GATHER>(c, a, sm_count, st);
+        case 128:
+            if (mode == wd::A_TMA) return launch_persist_t<128, 4, wd::A_TMA>(c, a, sm_count, st);
+            if (mode == wd::A_GATHER) return launch_persist_t<128, 4, wd::A_GATHER>(c, a, sm_count, st);
+            break;
+        case 256:
+            if (mode == wd::A_TMA) return launch_persist_t<256, 3, wd::A_TMA>(c, a, sm_count, st);
+            if (mode == wd::A_GATHER) return launch_persist_t<256, 3, wd::A_GATHER>(c, a, sm_count, st);
+            break;
+    }
+    return fail(WD_ERR_INVALID, "no persistent conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
+}
+
 int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
     const int mode = c.a_mode;
     switch (c.tile_n) {
@@ -326,6 +366,7 @@ wd::ConvArgs conv_args(const ConvLayer& c, const void* in, void* out, const void
     a.fold = c.fold;
     a.relu = c.relu;
     a.n_tiles = c.Cout / c.tile_n;
+    a.num_tiles = ((a.M + wd::kTileM - 1) / wd::kTileM) * a.n_tiles;
     return a;
 }
 
@@ -403,6 +444,14 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     return WD_OK;
 }
 
+// 2-D view {Cout, rows} of an output / residual buffer, box = 64 columns x 32 rows (one epilogue warp's slab).
+int make_omap(CUtensorMap* map, const void* base, int Cout, size_t rows) {
+    const uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)rows};
+    const uint64_t strides[1] = {(uint64_t)Cout * 2};
+    const uint32_t box[2] = {64, 32};
+    return make_tmap_bf16(map, base, 2, dims, strides, box);
+}
+
 // 3-D activation view {C, T=8, P} of a T-inner buffer for the A_TMA mode.
 int make_amap(CUtensorMap* map, const void* base, int Cin, size_t pixels) {
     const uint64_t dims[3] = {(uint64_t)Cin, 8, (uint64_t)pixels};
@@ -450,7 +499,10 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 WD_CUDA(cudaGetLastError());
             } else {
                 wd::ConvArgs a = conv_args(c, in, out, res, n_clips);
-                WD_TRY(launch_conv(c, a, st));
+                if (e->persistent)
+                    WD_TRY(launch_persist(c, a, e->sm_count, st));
+                else
+                    WD_TRY(launch_conv(c, a, st));
             }
             ++e->launches;
         } else if (o.kind == OP_MAXPOOL) {
@@ -579,6 +631,7 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
                     prop.minor);
     wd_engine* e = new wd_engine();
     e->desc = *d;
+    e->sm_count = prop.multiProcessorCount;
     e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
     int r = build_plan(e);
     if (r != WD_OK) {
@@ -625,6 +678,8 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     if (!e || !key) return fail(WD_ERR_INVALID, "engine/key NULL");
     if (!strcmp(key, "use_tma_a")) {
         e->use_tma_a = value ? 1 : 0;
+    } else if (!strcmp(key, "persistent")) {
+        e->persistent = value ? 1 : 0;
     } else if (!strcmp(key, "tile_n_max")) {
         if (value != 64 && value != 128 && value != 256) return fail(WD_ERR_INVALID, "tile_n_max must be 64/128/256");
         e->tile_n_max = value;
@@ -672,8 +727,11 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     // A-operand TMA views over the workspace buffers
     if (e->desc.mode == WD_MODE_BF16) {
         for (const Op& o : e->ops) {
-            if (o.kind != OP_CONV) continue;
+            if (o.kind != OP_CONV && o.kind != OP_STEM) continue;
             ConvLayer& c = e->convs[o.conv];
+            const size_t rows = (size_t)e->desc.max_clips * c.Hout * c.Wout * 8;
+            WD_TRY(make_omap(&c.omap, e->buf[o.out_buf], c.Cout, rows));
+            if (o.res_buf >= 0) WD_TRY(make_omap(&c.rmap, e->buf[o.res_buf], c.Cout, rows));
             if (c.a_mode != wd::A_TMA) continue;
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
         }
@@ -862,7 +920,7 @@ int64_t wd_engine_launch_count(const wd_engine* e) { return e ? e->launches : 0;
 
 int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
                   int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
-                  int tile_n) {
+                  int tile_n, int persistent) {
     if (!x || !w || !bias || !y) return fail(WD_ERR_INVALID, "NULL argument");
     ConvLayer c;
     c.name = "debug";
@@ -885,9 +943,14 @@ int wd_debug_conv(const void* x, const float* w, const float* bias, const void* 
     } else {
         if (a_mode != wd::A_TMA) c.a_mode = wd::A_GATHER;
         if (c.a_mode == wd::A_TMA) rc = make_amap(&c.amap, x, Cin, (size_t)clips * Hin * Win);
+        const size_t rows = (size_t)clips * c.Hout * c.Wout * 8;
+        if (rc == WD_OK) rc = make_omap(&c.omap, y, Cout, rows);
+        if (rc == WD_OK && residual) rc = make_omap(&c.rmap, residual, Cout, rows);
         if (rc == WD_OK) {
             wd::ConvArgs a = conv_args(c, x, y, residual, clips);
-            rc = launch_conv(c, a, nullptr);
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+            rc = persistent ? launch_persist(c, a, sms, nullptr) : launch_conv(c, a, nullptr);
         }
         if (rc == WD_OK) {
             cudaError_t ce = cudaDeviceSynchronize();

@@ -24,7 +24,8 @@ class Engine:
 
     def __init__(self, num_class: int, max_clips: int = 64, mode: str = "bf16", device: int = 0,
                  is_shift: bool = True, shift_div: int = 8, num_segments: int = 8,
-                 use_tma_a: Optional[bool] = None, tile_n_max: Optional[int] = None):
+                 use_tma_a: Optional[bool] = None, tile_n_max: Optional[int] = None,
+                 persistent: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("workoutdetector_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -43,6 +44,8 @@ class Engine:
             self.set_option("use_tma_a", int(use_tma_a))
         if tile_n_max is not None:
             self.set_option("tile_n_max", tile_n_max)
+        if persistent is not None:
+            self.set_option("persistent", int(persistent))
         self._tap = None
 
     def close(self):
@@ -198,7 +201,7 @@ def scores_to_states(scores: torch.Tensor, threshold: float = 0.5, softmax: bool
 
 
 def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor], stride: int,
-               fold: int, relu: bool, a_mode: str, tile_n: int) -> torch.Tensor:
+               fold: int, relu: bool, a_mode: str, tile_n: int, persistent: bool = True) -> torch.Tensor:
     """Test hook: one tcgen05 conv. x bf16 cuda [clips,H,W,8,Cin] (T-inner); w fp32 [Cout,Cin,k,k]."""
     lib = _lib.load()
     clips, Hin, Win, T, Cin = x.shape
@@ -211,5 +214,5 @@ def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: O
     bc = bias.detach().to("cpu", torch.float32).contiguous()
     torch.cuda.synchronize()
     check(lib.wd_debug_conv(_ptr(x), _ptr(wc), _ptr(bc), _ptr(residual), _ptr(y), clips, Hin, Win, Cin, Cout, k,
-                            stride, fold, int(relu), {"gather": 0, "tma": 2}[a_mode], tile_n))
+                            stride, fold, int(relu), {"gather": 0, "tma": 2}[a_mode], tile_n, int(persistent)))
     return y
