@@ -131,22 +131,30 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, 
 /* ---- introspection, tuning and test hooks (not part of the reference surface) ---- */
 int wd_engine_num_ops(const wd_engine* e);
 /* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head), Cin, Cout, ksize, stride, Hout, Wout, fold,
- *              a_mode (0 gather, 1 stem, 2 tma, -1 n/a), tile_n;   macs_per_clip = multiply-accumulates per clip */
+ *              a_mode (0 gather, 1 stem, 2 tma, 3 strip, -1 n/a), tile_n;   macs_per_clip = multiply-accumulates per clip */
 int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int32_t* info, double* macs_per_clip);
 /* After op `idx` runs in the next forwards, its output is converted to fp32 NCHW frames [n_clips*8, C, H, W]
  * at dst (device).  idx < 0 disables.  The head op (logits) cannot be tapped. */
 int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems);
-/* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (0/1: persistent vs one-tile-per-CTA kernel).  Takes effect at the next wd_engine_load_weights. */
+/* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (0: one tile per CTA, 1: persistent v2, 2: persistent v3 = default),
+ * "use_strip" (0/1: row-strip A operand for 3x3 stride-1 convolutions, v3 only).  Takes effect at the next wd_engine_load_weights. */
 int wd_engine_set_option(wd_engine* e, const char* key, int value);
 /* Number of kernels the engine launched since creation (all are this library's own kernels). */
 int64_t wd_engine_launch_count(const wd_engine* e);
 
 /* Run ONE convolution outside an engine (tests): x device bf16 T-inner [clips,Hin,Win,8,Cin], w host fp32
  * [Cout,Cin,k,k], bias host fp32 [Cout], residual device bf16 or NULL -> y device bf16 [clips,Hout,Wout,8,Cout].
- * a_mode: 0 gather, 2 TMA (1x1 stride 1 only); persistent selects the kernel variant.  Synchronous. */
+ * a_mode: 0 gather, 2 TMA (1x1 stride 1 only), 3 strip (3x3 stride 1, W multiple of 14; persistent=2 only);
+ * persistent selects the kernel generation (0, 1, 2).  Synchronous. */
 int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
                   int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
                   int tile_n, int persistent);
+
+/* As wd_debug_conv, then `iters` more back-to-back launches on the same buffers timed with CUDA events
+ * (ms_per_launch: host float).  Measurement hook for single layers. */
+int wd_bench_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
+                  int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
+                  int tile_n, int persistent, int iters, float* ms_per_launch);
 
 #ifdef __cplusplus
 }

@@ -204,15 +204,22 @@ CONV_CASES = [
     (3, 7, 128, 512, 1, 1, 0, 1, 1, "gather", 128),
     (40, 14, 256, 1024, 1, 1, 0, 1, 1, "tma", 256),       # 490 x 4 tiles: several tiles per persistent CTA
     (24, 14, 128, 128, 3, 1, 0, 1, 0, "gather", 128),     # 294 tiles through the gather producers
+    (2, 14, 256, 256, 3, 1, 0, 1, 0, "strip", 256),       # row-strip A operand (v3 only): 1 strip per image row
+    (3, 28, 128, 128, 3, 1, 0, 1, 0, "strip", 128),       # 2 strips per row, W ring (not resident)
+    (2, 56, 64, 64, 3, 1, 0, 1, 0, "strip", 64),          # 4 strips per row, W resident
+    (20, 28, 64, 256, 1, 1, 0, 1, 1, "tma", 256),         # W-resident 1x1 + residual ring across many tiles
+    (20, 28, 64, 256, 1, 1, 0, 1, 1, "tma", 128),
 ]
 
 
-@pytest.mark.parametrize("persistent", [True, False], ids=["persistent", "tile_per_cta"])
+@pytest.mark.parametrize("persistent", [2, 1, 0], ids=["v3", "v2", "tile_per_cta"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[f"c{i}" for i in range(len(CONV_CASES))])
 def test_conv_umma_vs_torch(case, persistent):
     from workoutdetector_b200.engine import debug_conv
     torch.backends.cudnn.allow_tf32 = False
     clips, H, Cin, Cout, k, stride, fold, relu, res, mode, tile_n = case
+    if mode == "strip" and persistent != 2:
+        pytest.skip("strip mode exists only in the v3 kernel")
     g = torch.Generator().manual_seed(1000 + CONV_CASES.index(case))
     x = torch.randn(clips, H, H, 8, Cin, generator=g).to(torch.bfloat16).cuda()
     w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16).float()

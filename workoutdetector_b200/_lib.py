@@ -64,6 +64,8 @@ SYMBOLS = {
     "wd_engine_set_option": (_i, [_vp, C.c_char_p, _i]),
     "wd_engine_launch_count": (C.c_int64, [_vp]),
     "wd_debug_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "wd_bench_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                           C.POINTER(C.c_float)]),
 }
 
 _lib = None

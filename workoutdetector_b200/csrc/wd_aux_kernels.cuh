@@ -218,7 +218,7 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ ou
 // so the whole head is one reduction over 392 rows followed by a [classes x 2048] mat-vec with warp-shuffle
 // reductions and a single-warp softmax.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadThreads = 256;
+constexpr int kHeadThreads = 1024;  // 256 channel groups (8 ch) x 4 row partitions
 constexpr int kMaxClasses = 1024;
 
 template <typename T>
@@ -231,24 +231,33 @@ head_kernel(const T* __restrict__ feat,  // [clips, rows_per_clip, C]
             float* __restrict__ probs,   // nullable
             int32_t* __restrict__ state  // nullable
 ) {
-    extern __shared__ float sm[];  // C feature means, then classes logits
+    extern __shared__ float sm[];  // C feature means, classes logits, then 4 x C partial sums
     float* sfeat = sm;
     float* slog = sm + C;
+    float* spart = slog + classes;
     const int n = blockIdx.x;
     const T* base = feat + (size_t)n * rows_per_clip * C;
     const float inv = 1.0f / (float)rows_per_clip;
-    // phase 1: column means. thread owns channel groups of 8.
-    for (int c8 = threadIdx.x; c8 < C / 8; c8 += kHeadThreads) {
+    // phase 1: column means. thread = (channel group of 8, one of 4 row partitions); 16-byte loads, 4x the loads
+    // in flight per SM compared with one partition.
+    const int part = threadIdx.x >> 8;
+    const int rows_per_part = (rows_per_clip + 3) / 4;
+    const int r0 = part * rows_per_part;
+    const int r1 = min(r0 + rows_per_part, rows_per_clip);
+    for (int c8 = threadIdx.x & 255; c8 < C / 8; c8 += 256) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int r = 0; r < rows_per_clip; ++r) {
+        for (int r = r0; r < r1; ++r) {
             float v[8];
             load8(base + (size_t)r * C + c8 * 8, v);
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] += v[q];
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sfeat[c8 * 8 + q] = acc[q] * inv;
+        for (int q = 0; q < 8; ++q) spart[part * C + c8 * 8 + q] = acc[q];
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kHeadThreads)
+        sfeat[c] = (spart[c] + spart[C + c] + spart[2 * C + c] + spart[3 * C + c]) * inv;
     __syncthreads();
     // phase 2: one warp per class (strided), shuffle-reduced dot product.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

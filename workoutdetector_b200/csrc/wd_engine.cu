@@ -17,6 +17,7 @@
 #include "wd_aux_kernels.cuh"
 #include "wd_conv_persistent.cuh"
 #include "wd_conv_umma.cuh"
+#include "wd_conv_v3.cuh"
 
 namespace {
 
@@ -115,6 +116,7 @@ struct ConvLayer {
     CUtensorMap amap;
     CUtensorMap omap;  // output [rows, Cout], box {64, 32} (persistent kernel's TMA store)
     CUtensorMap rmap;  // residual, same geometry
+    CUtensorMap omap16;  // output, box {64, 16}: last warp of a 112-row strip tile
 };
 
 struct Op {
@@ -135,7 +137,8 @@ struct wd_engine {
     bool weights_loaded = false;
     int use_tma_a = 1;
     int tile_n_max = 256;
-    int persistent = 1;
+    int persistent = 2;  // 0: one tile per CTA, 1: persistent v2, 2: persistent v3 (W-resident, strip 3x3)
+    int use_strip = 1;
     int sm_count = 148;
     std::vector<ConvLayer> convs;
     std::vector<Op> ops;
@@ -326,6 +329,101 @@ int launch_persist(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cuda
     return fail(WD_ERR_INVALID, "no persistent conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
 }
 
+// Shared-memory plan of conv_v3_kernel for one layer (see wd_conv_v3.cuh).
+struct SmemPlan {
+    int a_stages, b_stages, w_resident, a_stage_bytes, off_b, off_out, off_res, off_bar, total;
+};
+
+int plan_smem(int BN, int mode, int kblocks, bool has_res, bool grid_keeps_n_tile, SmemPlan* out) {
+    const int kMaxDynamic = 232448;  // 227 KiB opt-in limit per CTA on sm_100
+    const int btile = BN * 128;
+    const bool strip = mode == wd::A_STRIP;
+    const int a_stage = strip ? wd::kStripStage : wd::kATileBytes;
+    const int out_b = 8 * wd::kEpiSlab;
+    const int res_b = has_res ? 4 * wd::kResDepth * wd::kEpiSlab : 0;
+    const int bars = 1024;
+    const int avail = kMaxDynamic - 1024 - out_b - res_b - bars;
+    SmemPlan p{};
+    p.a_stage_bytes = a_stage;
+    const int wbytes = kblocks * btile;
+    p.w_resident = grid_keeps_n_tile && wbytes <= 73728 && (avail - wbytes) / a_stage >= 2;
+    if (p.w_resident) {
+        p.a_stages = std::min(8, (avail - wbytes) / a_stage);
+        p.b_stages = 1;
+    } else if (strip) {
+        p.a_stages = 2;
+        p.b_stages = std::min(8, (avail - 2 * a_stage) / btile);
+    } else {
+        p.a_stages = p.b_stages = std::min(8, avail / (a_stage + btile));
+    }
+    if (p.a_stages < 2 || p.b_stages < 1 || (!p.w_resident && p.b_stages < 2))
+        return fail(WD_ERR_INVALID, "no shared-memory plan for BN=%d mode=%d kblocks=%d", BN, mode, kblocks);
+    p.off_b = p.a_stages * a_stage;
+    p.off_out = p.off_b + (p.w_resident ? wbytes : p.b_stages * btile);
+    p.off_res = p.off_out + out_b;
+    p.off_bar = p.off_res + res_b;
+    p.total = p.off_bar + bars + 1024;
+    *out = p;
+    return WD_OK;
+}
+
+template <int BN, int AMODE>
+int launch_v3_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_v3_kernel<BN, AMODE>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::ConvArgs3 p{};
+    p.c = a;
+    int grid = std::min(a.num_tiles, sm_count);
+    const bool keeps = grid >= a.n_tiles;
+    if (keeps) grid = (grid / a.n_tiles) * a.n_tiles;
+    SmemPlan sp;
+    WD_TRY(plan_smem(BN, AMODE, a.kblocks, a.residual != nullptr, keeps, &sp));
+    p.a_stages = sp.a_stages;
+    p.b_stages = sp.b_stages;
+    p.w_resident = sp.w_resident;
+    p.a_stage_bytes = sp.a_stage_bytes;
+    p.off_b = sp.off_b;
+    p.off_out = sp.off_out;
+    p.off_res = sp.off_res;
+    p.off_bar = sp.off_bar;
+    p.tiles_w = AMODE == wd::A_STRIP ? a.Wout / wd::kStripPixels : 1;
+    const unsigned threads = (AMODE == wd::A_TMA || AMODE == wd::A_STRIP) ? 224 : 320;
+    kfn<<<(unsigned)grid, threads, sp.total, st>>>(c.wmap, c.amap, c.omap, c.rmap, c.omap16, p);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int launch_v3(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    const int mode = c.a_mode;
+    if (mode == wd::A_STRIP) {  // tiles are 14-pixel row segments
+        a.num_tiles = (a.M / wd::kStripRows) * a.n_tiles;
+    }
+    switch (c.tile_n) {
+        case 64:
+            if (mode == wd::A_STEM) return launch_v3_t<64, wd::A_STEM>(c, a, sm_count, st);
+            if (mode == wd::A_TMA) return launch_v3_t<64, wd::A_TMA>(c, a, sm_count, st);
+            if (mode == wd::A_STRIP) return launch_v3_t<64, wd::A_STRIP>(c, a, sm_count, st);
+            return launch_v3_t<64, wd::A_GATHER>(c, a, sm_count, st);
+        case 128:
+            if (mode == wd::A_TMA) return launch_v3_t<128, wd::A_TMA>(c, a, sm_count, st);
+            if (mode == wd::A_STRIP) return launch_v3_t<128, wd::A_STRIP>(c, a, sm_count, st);
+            if (mode == wd::A_GATHER) return launch_v3_t<128, wd::A_GATHER>(c, a, sm_count, st);
+            break;
+        case 256:
+            if (mode == wd::A_TMA) return launch_v3_t<256, wd::A_TMA>(c, a, sm_count, st);
+            if (mode == wd::A_STRIP) return launch_v3_t<256, wd::A_STRIP>(c, a, sm_count, st);
+            if (mode == wd::A_GATHER) return launch_v3_t<256, wd::A_GATHER>(c, a, sm_count, st);
+            break;
+    }
+    return fail(WD_ERR_INVALID, "no v3 conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
+}
+
+int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st);
+
 int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
     const int mode = c.a_mode;
     switch (c.tile_n) {
@@ -343,6 +441,13 @@ int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
             break;
     }
     return fail(WD_ERR_INVALID, "no conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
+}
+
+int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st) {
+    if (version >= 2) return launch_v3(c, a, sm_count, st);
+    if (c.a_mode == wd::A_STRIP) return fail(WD_ERR_INVALID, "strip mode needs the v3 kernel");
+    if (version == 1) return launch_persist(c, a, sm_count, st);
+    return launch_conv(c, a, st);
 }
 
 wd::ConvArgs conv_args(const ConvLayer& c, const void* in, void* out, const void* res, int clips) {
@@ -373,7 +478,7 @@ wd::ConvArgs conv_args(const ConvLayer& c, const void* in, void* out, const void
 // Fold BN into (w, bias) on the host and upload in the layout of the engine's mode.
 //   w: [Cout, Cin, k, k] fp32; scale/shift: [Cout]
 int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const float* w, const float* scale,
-                const float* shift) {
+                const float* shift, int use_strip = 0) {
     const int K = c.Cin * c.k * c.k;
     if (c.w_packed) cudaFree(c.w_packed);
     if (c.bias) cudaFree(c.bias);
@@ -433,6 +538,8 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
         c.a_mode = wd::A_STEM;
     else if (use_tma_a && c.k == 1 && c.stride == 1 && (c.fold == 0 || c.fold % 64 == 0))
         c.a_mode = wd::A_TMA;
+    else if (use_strip && c.k == 3 && c.stride == 1 && c.Wout % wd::kStripPixels == 0 && c.Wout >= wd::kStripPixels)
+        c.a_mode = wd::A_STRIP;
     else
         c.a_mode = wd::A_GATHER;
     WD_CUDA(cudaMalloc(&c.w_packed, p.size() * 2));
@@ -445,11 +552,20 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
 }
 
 // 2-D view {Cout, rows} of an output / residual buffer, box = 64 columns x 32 rows (one epilogue warp's slab).
-int make_omap(CUtensorMap* map, const void* base, int Cout, size_t rows) {
+int make_omap(CUtensorMap* map, const void* base, int Cout, size_t rows, int box_rows = 32) {
     const uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)rows};
     const uint64_t strides[1] = {(uint64_t)Cout * 2};
-    const uint32_t box[2] = {64, 32};
+    const uint32_t box[2] = {64, (uint32_t)box_rows};
     return make_tmap_bf16(map, base, 2, dims, strides, box);
+}
+
+// 5-D activation view {C, T=8, W, H, clips} for A_STRIP: box = 64 channels x 8 segments x 16 pixels of one row.
+int make_amap5(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t clips) {
+    const uint64_t dims[5] = {(uint64_t)Cin, 8, (uint64_t)W, (uint64_t)H, (uint64_t)clips};
+    const uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16, (uint64_t)W * Cin * 16,
+                                 (uint64_t)H * W * Cin * 16};
+    const uint32_t box[5] = {64, 8, 16, 1, 1};
+    return make_tmap_bf16(map, base, 5, dims, strides, box);
 }
 
 // 3-D activation view {C, T=8, P} of a T-inner buffer for the A_TMA mode.
@@ -499,10 +615,7 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 WD_CUDA(cudaGetLastError());
             } else {
                 wd::ConvArgs a = conv_args(c, in, out, res, n_clips);
-                if (e->persistent)
-                    WD_TRY(launch_persist(c, a, e->sm_count, st));
-                else
-                    WD_TRY(launch_conv(c, a, st));
+                WD_TRY(launch_any(c, a, e->persistent, e->sm_count, st));
             }
             ++e->launches;
         } else if (o.kind == OP_MAXPOOL) {
@@ -521,7 +634,7 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
             const ConvLayer& last = e->convs.back();
             const int rows = last.Hout * last.Wout * 8;
             const int C = last.Cout;
-            const size_t smem = (size_t)(C + e->desc.num_class) * sizeof(float);
+            const size_t smem = (size_t)(5 * C + e->desc.num_class) * sizeof(float);
             if (f32)
                 wd::head_kernel<float><<<n_clips, wd::kHeadThreads, smem, st>>>(
                     static_cast<const float*>(in), e->fc_w, e->fc_b, rows, C, e->desc.num_class, threshold,
@@ -679,7 +792,10 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     if (!strcmp(key, "use_tma_a")) {
         e->use_tma_a = value ? 1 : 0;
     } else if (!strcmp(key, "persistent")) {
-        e->persistent = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(WD_ERR_INVALID, "persistent must be 0, 1 or 2");
+        e->persistent = value;
+    } else if (!strcmp(key, "use_strip")) {
+        e->use_strip = value ? 1 : 0;
     } else if (!strcmp(key, "tile_n_max")) {
         if (value != 64 && value != 128 && value != 256) return fail(WD_ERR_INVALID, "tile_n_max must be 64/128/256");
         e->tile_n_max = value;
@@ -722,7 +838,8 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             scale[i] = s;
             shift[i] = b[i] - mu[i] * s;
         }
-        WD_TRY(upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, w, scale.data(), shift.data()));
+        WD_TRY(upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, w, scale.data(), shift.data(),
+                           e->persistent >= 2 ? e->use_strip : 0));
     }
     // A-operand TMA views over the workspace buffers
     if (e->desc.mode == WD_MODE_BF16) {
@@ -732,6 +849,10 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             const size_t rows = (size_t)e->desc.max_clips * c.Hout * c.Wout * 8;
             WD_TRY(make_omap(&c.omap, e->buf[o.out_buf], c.Cout, rows));
             if (o.res_buf >= 0) WD_TRY(make_omap(&c.rmap, e->buf[o.res_buf], c.Cout, rows));
+            if (c.a_mode == wd::A_STRIP) {
+                WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
+                WD_TRY(make_amap5(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
+            }
             if (c.a_mode != wd::A_TMA) continue;
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
         }
@@ -918,9 +1039,9 @@ int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t cap) {
 
 int64_t wd_engine_launch_count(const wd_engine* e) { return e ? e->launches : 0; }
 
-int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
-                  int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
-                  int tile_n, int persistent) {
+static int debug_conv_impl(const void* x, const float* w, const float* bias, const void* residual, void* y,
+                           int clips, int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu,
+                           int a_mode, int tile_n, int persistent, int iters, float* ms_out) {
     if (!x || !w || !bias || !y) return fail(WD_ERR_INVALID, "NULL argument");
     ConvLayer c;
     c.name = "debug";
@@ -936,13 +1057,18 @@ int wd_debug_conv(const void* x, const float* w, const float* bias, const void* 
     c.fold = fold;
     c.relu = relu;
     std::vector<float> ones(Cout, 1.0f);
-    WD_TRY(upload_conv(c, WD_MODE_BF16, tile_n, a_mode == wd::A_TMA ? 1 : 0, w, ones.data(), bias));
+    WD_TRY(upload_conv(c, WD_MODE_BF16, tile_n, a_mode == wd::A_TMA ? 1 : 0, w, ones.data(), bias,
+                       a_mode == wd::A_STRIP ? 1 : 0));
     int rc = WD_OK;
-    if (a_mode == wd::A_TMA && c.a_mode != wd::A_TMA) {
-        rc = fail(WD_ERR_INVALID, "shape not eligible for the TMA A-operand path");
+    if ((a_mode == wd::A_TMA || a_mode == wd::A_STRIP) && c.a_mode != a_mode) {
+        rc = fail(WD_ERR_INVALID, "shape not eligible for the requested A-operand path");
     } else {
-        if (a_mode != wd::A_TMA) c.a_mode = wd::A_GATHER;
+        if (a_mode != wd::A_TMA && a_mode != wd::A_STRIP) c.a_mode = wd::A_GATHER;
         if (c.a_mode == wd::A_TMA) rc = make_amap(&c.amap, x, Cin, (size_t)clips * Hin * Win);
+        if (c.a_mode == wd::A_STRIP) {
+            rc = make_amap5(&c.amap, x, Cin, Win, Hin, (size_t)clips);
+            if (rc == WD_OK) rc = make_omap(&c.omap16, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 16);
+        }
         const size_t rows = (size_t)clips * c.Hout * c.Wout * 8;
         if (rc == WD_OK) rc = make_omap(&c.omap, y, Cout, rows);
         if (rc == WD_OK && residual) rc = make_omap(&c.rmap, residual, Cout, rows);
@@ -950,7 +1076,22 @@ int wd_debug_conv(const void* x, const float* w, const float* bias, const void* 
             wd::ConvArgs a = conv_args(c, x, y, residual, clips);
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-            rc = persistent ? launch_persist(c, a, sms, nullptr) : launch_conv(c, a, nullptr);
+            rc = launch_any(c, a, persistent, sms, nullptr);
+            if (rc == WD_OK && iters > 0 && ms_out) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                for (int i = 0; i < 2 && rc == WD_OK; ++i) rc = launch_any(c, a, persistent, sms, nullptr);
+                cudaEventRecord(e0, nullptr);
+                for (int i = 0; i < iters && rc == WD_OK; ++i) rc = launch_any(c, a, persistent, sms, nullptr);
+                cudaEventRecord(e1, nullptr);
+                cudaEventSynchronize(e1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e0, e1);
+                *ms_out = ms / iters;
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+            }
         }
         if (rc == WD_OK) {
             cudaError_t ce = cudaDeviceSynchronize();
@@ -960,6 +1101,21 @@ int wd_debug_conv(const void* x, const float* w, const float* bias, const void* 
     cudaFree(c.w_packed);
     cudaFree(c.bias);
     return rc;
+}
+
+int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
+                  int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
+                  int tile_n, int persistent) {
+    return debug_conv_impl(x, w, bias, residual, y, clips, Hin, Win, Cin, Cout, ksize, stride, fold, relu, a_mode,
+                           tile_n, persistent, 0, nullptr);
+}
+
+int wd_bench_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
+                  int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
+                  int tile_n, int persistent, int iters, float* ms_per_launch) {
+    if (iters < 1 || !ms_per_launch) return fail(WD_ERR_INVALID, "iters/ms_per_launch");
+    return debug_conv_impl(x, w, bias, residual, y, clips, Hin, Win, Cin, Cout, ksize, stride, fold, relu, a_mode,
+                           tile_n, persistent, iters, ms_per_launch);
 }
 
 }  // extern "C"

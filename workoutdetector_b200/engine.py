@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import MODE_BF16, MODE_FP32_VALIDATE, ModelDesc, NamedTensor, check
 
 OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head"}
-A_MODES = {0: "gather", 1: "stem", 2: "tma", -1: "-"}
+A_MODES = {0: "gather", 1: "stem", 2: "tma", 3: "strip", -1: "-"}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -25,7 +25,7 @@ class Engine:
     def __init__(self, num_class: int, max_clips: int = 64, mode: str = "bf16", device: int = 0,
                  is_shift: bool = True, shift_div: int = 8, num_segments: int = 8,
                  use_tma_a: Optional[bool] = None, tile_n_max: Optional[int] = None,
-                 persistent: Optional[bool] = None):
+                 persistent: Optional[int] = None, use_strip: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("workoutdetector_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -46,6 +46,8 @@ class Engine:
             self.set_option("tile_n_max", tile_n_max)
         if persistent is not None:
             self.set_option("persistent", int(persistent))
+        if use_strip is not None:
+            self.set_option("use_strip", int(use_strip))
         self._tap = None
 
     def close(self):
@@ -201,7 +203,7 @@ def scores_to_states(scores: torch.Tensor, threshold: float = 0.5, softmax: bool
 
 
 def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor], stride: int,
-               fold: int, relu: bool, a_mode: str, tile_n: int, persistent: bool = True) -> torch.Tensor:
+               fold: int, relu: bool, a_mode: str, tile_n: int, persistent: int = 2) -> torch.Tensor:
     """Test hook: one tcgen05 conv. x bf16 cuda [clips,H,W,8,Cin] (T-inner); w fp32 [Cout,Cin,k,k]."""
     lib = _lib.load()
     clips, Hin, Win, T, Cin = x.shape
@@ -214,5 +216,22 @@ def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: O
     bc = bias.detach().to("cpu", torch.float32).contiguous()
     torch.cuda.synchronize()
     check(lib.wd_debug_conv(_ptr(x), _ptr(wc), _ptr(bc), _ptr(residual), _ptr(y), clips, Hin, Win, Cin, Cout, k,
-                            stride, fold, int(relu), {"gather": 0, "tma": 2}[a_mode], tile_n, int(persistent)))
+                            stride, fold, int(relu), {"gather": 0, "tma": 2, "strip": 3}[a_mode], tile_n, int(persistent)))
     return y
+
+
+def bench_conv(clips: int, H: int, Cin: int, Cout: int, k: int, stride: int, fold: int, residual: bool, a_mode: str,
+               tile_n: int, persistent: int = 2, iters: int = 20) -> float:
+    """Measurement hook: milliseconds per launch of one conv layer shape on random data (CUDA events)."""
+    lib = _lib.load()
+    x = torch.randn(clips, H, H, 8, Cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k) / (Cin * k * k) ** 0.5).contiguous()
+    b = torch.randn(Cout)
+    Ho = (H + 2 * (k // 2) - k) // stride + 1
+    r = torch.randn(clips, Ho, Ho, 8, Cout, device="cuda").to(torch.bfloat16) if residual else None
+    y = torch.empty((clips, Ho, Ho, 8, Cout), dtype=torch.bfloat16, device="cuda")
+    ms = C.c_float()
+    torch.cuda.synchronize()
+    check(lib.wd_bench_conv(_ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), clips, H, H, Cin, Cout, k, stride, fold, 1,
+                            {"gather": 0, "tma": 2, "strip": 3}[a_mode], tile_n, int(persistent), iters, C.byref(ms)))
+    return ms.value
