@@ -212,14 +212,14 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("persistent", [2, 1, 0], ids=["v3", "v2", "tile_per_cta"])
+@pytest.mark.parametrize("persistent", [3, 2, 1, 0], ids=["v4", "v3", "v2", "tile_per_cta"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[f"c{i}" for i in range(len(CONV_CASES))])
 def test_conv_umma_vs_torch(case, persistent):
     from workoutdetector_b200.engine import debug_conv
     torch.backends.cudnn.allow_tf32 = False
     clips, H, Cin, Cout, k, stride, fold, relu, res, mode, tile_n = case
-    if mode == "strip" and persistent != 2:
-        pytest.skip("strip mode exists only in the v3 kernel")
+    if mode == "strip" and persistent < 2:
+        pytest.skip("strip mode exists only in the v3/v4 kernels")
     g = torch.Generator().manual_seed(1000 + CONV_CASES.index(case))
     x = torch.randn(clips, H, H, 8, Cin, generator=g).to(torch.bfloat16).cuda()
     w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16).float()

@@ -31,7 +31,7 @@ if __name__ == "__main__":
         for clips in clip_list:
             for ver in versions:
                 modes = [mode]
-                if ver == 2 and k == 3 and stride == 1 and H % 14 == 0:
+                if ver >= 2 and k == 3 and stride == 1 and H % 14 == 0:
                     modes.append("strip")
                 for md in modes:
                     try:

@@ -1,0 +1,432 @@
+// wd_conv_v4.cuh — fourth generation of the persistent implicit-GEMM convolution (sm_100a).
+//
+// Same GEMM view, layouts, A-operand modes and shared-memory plan as wd_conv_v3.cuh.  What changed, and the
+// evidence (profiles/r01_ncu_layers_v3.txt, ncu --set full of three single-layer launches at batch 64):
+//   * The MMA issuer was the bottleneck of EVERY layer: warp sampling showed the epilogue warps parked on
+//     tmem_full while the issuing thread spent ~80 cycles per tcgen05.mma — `if (lane == 0)` inside a branch on
+//     threadIdx-derived `warp` is divergent code to the compiler, so each UTCHMMA was wrapped in an
+//     ELECT / R2UR.BROADCAST / BRA.U.ANY loop.  Here the warp index comes from a shuffle (warp-uniform), every
+//     role loop runs with all 32 lanes converged, descriptors live in uniform registers and the instruction is
+//     issued under elect.sync: four UTCHMMA back to back per k-block (checked with cuobjdump -sass).
+//     The same holds for UTMALDG / UTMASTG / UTCBAR in the producers and the epilogue.
+//   * The epilogue of the residual layers was latency-bound (one warp per scheduler, each 8-column step waited
+//     for its own LDS/LDG because stores to the out slab may alias the residual slab).  All loads of a 64-column
+//     chunk (residual, bias from shared memory, accumulator) are now issued before the first store; ReLU is
+//     folded into the bf16 pack (cvt.rn.relu.bf16x2.f32); the bias of the CTA's n-tile is staged in shared memory
+//     once per CTA.
+//   * HAS_RES is a template parameter (no per-element branch).
+#pragma once
+#include "wd_conv_v3.cuh"
+
+namespace wd {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo));
+    return o;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t o;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo));
+    return o;
+}
+
+// hi/lo 32-bit halves of the K-major SWIZZLE_128B descriptor: hi is constant, lo carries the address.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024, version 1, layout 2
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
+    return (static_cast<uint64_t>(kDescHiSw128) << 32) | lo;
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+    return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+
+template <int BN, int AMODE, bool HAS_RES>
+__global__ void __launch_bounds__((AMODE == A_TMA || AMODE == A_STRIP) ? 224 : 320, 1)
+conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
+               const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap rmap,
+               const __grid_constant__ CUtensorMap omap16, const ConvArgs3 p) {
+    constexpr int kBTile = BN * kTileK * 2;
+    constexpr bool kStrip = (AMODE == A_STRIP);
+    constexpr bool kTmaA = (AMODE == A_TMA || AMODE == A_STRIP);
+    constexpr int kTaps = kStrip ? 9 : 1;  // W steps per A stage
+    const ConvArgs& a = p.c;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + p.off_b;
+    uint8_t* sOut = smem + p.off_out;
+    uint8_t* sRes = smem + p.off_res;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    uint64_t* a_full = bars;                  // [8]
+    uint64_t* a_empty = bars + 8;             // [8]
+    uint64_t* b_full = bars + 16;             // [8]
+    uint64_t* b_empty = bars + 24;            // [8]
+    uint64_t* tmem_full_bar = bars + 32;      // [2]
+    uint64_t* tmem_empty_bar = bars + 34;     // [2]
+    uint64_t* w_bar = bars + 36;              // [1]
+    uint64_t* res_bar = bars + 40;            // [4 warps][kResDepth]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 56);
+    float* sBias = reinterpret_cast<float*>(bars + 64);  // BN floats (the plan reserves 2 KiB for barriers + bias)
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+    const int lane = tid & 31;
+    const int num_tiles = a.num_tiles;
+    const int a_steps = kStrip ? a.cin_blocks : a.kblocks;  // A stages per tile
+    const int cta_n0 = ((int)blockIdx.x % a.n_tiles) * BN;  // the grid is a multiple of n_tiles: one n-tile per CTA
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&wmap);
+            tma_prefetch_desc(&omap);
+            if (kTmaA) tma_prefetch_desc(&amap);
+            if (HAS_RES) tma_prefetch_desc(&rmap);
+            if (kStrip) tma_prefetch_desc(&omap16);
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(&a_full[s], kTmaA ? 1 : 128);
+                mbar_init(&a_empty[s], 1);
+                mbar_init(&b_full[s], 1);
+                mbar_init(&b_empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            mbar_init(w_bar, 1);
+            for (int s = 0; s < 4 * kResDepth; ++s) mbar_init(&res_bar[s], 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_ptr, 2 * BN);
+        tmem_relinquish();
+    }
+    if (warp < 4) {
+        for (int i = tid; i < BN; i += 128) sBias[i] = a.bias[cta_n0 + i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // tile -> first output row of the tile
+    auto tile_m0 = [&](int m_tile) -> int {
+        if (kStrip) {
+            const int ws = m_tile % p.tiles_w;
+            const int q = m_tile / p.tiles_w;  // n*H + h
+            return (q * a.Wout + ws * kStripPixels) * 8;
+        }
+        return m_tile * kTileM;
+    };
+
+    if (warp < 4) {
+        // ==========================================================================================
+        // Epilogue warps: TMEM -> (+bias, +residual, ReLU) -> bf16 -> swizzled smem slab -> TMA store
+        // ==========================================================================================
+        uint8_t* my_out = sOut + warp * 2 * kEpiSlab;
+        uint8_t* my_res = sRes + warp * kResDepth * kEpiSlab;
+        uint64_t* my_res_bar = res_bar + warp * kResDepth;
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        constexpr int kChunks = BN / 64;
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const uint32_t total_chunks = (uint32_t)my_tiles * kChunks;
+        uint32_t res_issue = 0;  // next residual chunk to request
+        uint32_t chunk_idx = 0;  // running chunk counter across tiles
+        int tile_iter = 0;
+        const bool relu = a.relu != 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int mrow = tile_m0(tile / a.n_tiles) + warp * 32;
+            const int acc = tile_iter & 1;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c, ++chunk_idx) {
+                __syncwarp();  // every lane is done with the ring slots about to be refilled
+                if (HAS_RES) {
+                    // keep the residual ring full: up to kResDepth chunks ahead, across tile boundaries
+                    while (res_issue < total_chunks && res_issue < chunk_idx + kResDepth) {
+                        const uint32_t slot = res_issue % kResDepth;
+                        const int t2 = (int)blockIdx.x + (int)(res_issue / kChunks) * (int)gridDim.x;
+                        const int rn0 = cta_n0 + (int)(res_issue % kChunks) * 64;
+                        const int rm = tile_m0(t2 / a.n_tiles) + warp * 32;
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&my_res_bar[slot], kEpiSlab);
+                            tma_load_2d(&rmap, &my_res_bar[slot], my_res + slot * kEpiSlab, rn0, rm);
+                        }
+                        __syncwarp();
+                        ++res_issue;
+                    }
+                }
+                if (c == 0) {
+                    mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+                    tc_fence_after_sync();
+                }
+                // ---- all loads of this chunk first: residual slab, bias, accumulator ----
+                uint4 rr[8];
+                const uint32_t rslot = chunk_idx % kResDepth;
+                if (HAS_RES) {
+                    mbar_wait(&my_res_bar[rslot], (chunk_idx / kResDepth) & 1);
+                    const uint8_t* rbuf = my_res + rslot * kEpiSlab + row_off;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) rr[u] = *reinterpret_cast<const uint4*>(rbuf + ((u ^ sw) << 4));
+                }
+                float4 bb[16];
+                const float4* bsrc = reinterpret_cast<const float4*>(sBias + c * 64);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * 64, v0);
+                tmem_ld32(taddr + c * 64 + 32, v1);
+                tmem_ld_wait();
+                if (c == kChunks - 1) {  // accumulator drained: hand it back to the MMA issuer
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                    __syncwarp();
+                }
+                if (elect_one()) tma_store_wait_read1();  // the store that last read this out slot is done reading
+                __syncwarp();
+                uint8_t* obuf = my_out + (chunk_idx & 1) * kEpiSlab + row_off;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t* v = (u < 4) ? (v0 + u * 8) : (v1 + (u - 4) * 8);
+                    const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                    float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                  __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                  __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                  __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    if (HAS_RES) {
+                        const uint32_t rw[4] = {rr[u].x, rr[u].y, rr[u].z, rr[u].w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            f[2 * q] += __uint_as_float(rw[q] << 16);
+                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t o[4];
+                    if (relu) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2_relu(f[2 * q], f[2 * q + 1]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    // strip tiles have 112 rows: the last warp stores a 16-row box so it never touches the next strip
+                    if (kStrip && warp == 3)
+                        tma_store_2d(&omap16, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                    else
+                        tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp == 4) {
+        // ==========================================================================================
+        // W producer
+        // ==========================================================================================
+        if (p.w_resident) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(w_bar, (uint32_t)a.kblocks * kBTile);
+                for (int kb = 0; kb < a.kblocks; ++kb)
+                    tma_load_2d(&wmap, w_bar, sB + kb * kBTile, kb * kTileK, cta_n0);
+            }
+            __syncwarp();
+        } else {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int as = 0; as < a_steps; ++as) {
+                    for (int tap = 0; tap < kTaps; ++tap, ++it) {
+                        const int slot = it % p.b_stages;
+                        mbar_wait(&b_empty[slot], ((it / p.b_stages) & 1) ^ 1);
+                        const int kbi = kStrip ? tap * a.cin_blocks + as : as;
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&b_full[slot], kBTile);
+                            tma_load_2d(&wmap, &b_full[slot], sB + slot * kBTile, kbi * kTileK, cta_n0);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ==========================================================================================
+        // MMA issuer: all 32 lanes run the loop (uniform registers), one elected lane issues
+        // ==========================================================================================
+        constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+        const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
+        const uint32_t sB_lo = umma_desc_lo(smem_u32(sB));
+        uint32_t ita = 0, itb = 0;
+        int tile_iter = 0;
+        if (p.w_resident) mbar_wait(w_bar, 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int acc = tile_iter & 1;
+            mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int as = 0; as < a_steps; ++as, ++ita) {
+                const int aslot = ita % p.a_stages;
+                mbar_wait(&a_full[aslot], (ita / p.a_stages) & 1);
+                if (!kTmaA) fence_proxy_async_smem();
+                tc_fence_after_sync();
+                const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * p.a_stage_bytes) >> 4);
+#pragma unroll 1
+                for (int tap = 0; tap < kTaps; ++tap) {
+                    uint32_t b_lo;
+                    int bslot = 0;
+                    const int kbi = kStrip ? tap * a.cin_blocks + as : as;
+                    if (p.w_resident) {
+                        b_lo = sB_lo + ((uint32_t)(kbi * kBTile) >> 4);
+                    } else {
+                        bslot = itb % p.b_stages;
+                        mbar_wait(&b_full[bslot], (itb / p.b_stages) & 1);
+                        tc_fence_after_sync();
+                        b_lo = sB_lo + ((uint32_t)(bslot * kBTile) >> 4);
+                        ++itb;
+                    }
+                    // strip: tap (r, s) = row slot r, shifted by s pixels (one pixel = one 1024-byte atom)
+                    const uint32_t at_lo = kStrip ? a_lo + (uint32_t)((tap / 3) * (16384 >> 4) + (tap % 3) * (1024 >> 4))
+                                                  : a_lo;
+                    const uint64_t adesc = umma_desc_from_lo(at_lo);
+                    const uint64_t bdesc = umma_desc_from_lo(b_lo);
+                    const uint32_t first = (as | tap) != 0 ? 1u : 0u;
+                    if (elect_one()) {
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, first);
+#pragma unroll
+                        for (int k = 1; k < kTileK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                        if (!p.w_resident) umma_commit(&b_empty[bslot]);
+                        if (tap == kTaps - 1) {
+                            umma_commit(&a_empty[aslot]);
+                            if (as == a_steps - 1) umma_commit(&tmem_full_bar[acc]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (kTmaA) {
+        // ==========================================================================================
+        // A producer by TMA (warp 6)
+        // ==========================================================================================
+        if (warp == 6) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / a.n_tiles;
+                for (int as = 0; as < a_steps; ++as, ++it) {
+                    const int slot = it % p.a_stages;
+                    mbar_wait(&a_empty[slot], ((it / p.a_stages) & 1) ^ 1);
+                    uint8_t* dst = sA + slot * p.a_stage_bytes;
+                    if (elect_one()) {
+                        if (kStrip) {
+                            const int ws = m_tile % p.tiles_w;
+                            const int q = m_tile / p.tiles_w;
+                            const int h = q % a.Hout;
+                            const int n = q / a.Hout;
+                            mbar_arrive_expect_tx(&a_full[slot], 3 * 16384);
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)  // rows h-1, h, h+1; pixels w0-1 .. w0+14; OOB -> zeros (padding)
+                                tma_load_5d(&amap, &a_full[slot], dst + r * 16384, as * kTileK, 0,
+                                            ws * kStripPixels - 1, h - 1 + r, n);
+                        } else {
+                            const int c = as * kTileK;
+                            int dt = 0;
+                            if (a.fold) dt = (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
+                            mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
+                            tma_load_3d(&amap, &a_full[slot], dst, c, dt, (m_tile * kTileM) >> 3);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ==========================================================================================
+        // A gather producers (warps 6-9): 16-byte cp.async with zero fill into the swizzled A stage
+        // ==========================================================================================
+        const int ptid = tid - 192;
+        const int j = ptid & 7;
+        const int rsub = ptid >> 3;
+        const int t = rsub & 7;
+        const uint32_t dst_thread = smem_u32(sA) + rsub * 128 + ((j ^ (rsub & 7)) << 4);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / a.n_tiles) * kTileM;
+            int ih0[8], iw0[8], base[8];
+            bool rowok[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + i * 16 + rsub;
+                rowok[i] = m < a.M;
+                const int pp = (rowok[i] ? m : 0) >> 3;
+                const int ow = pp % a.Wout;
+                const int q = pp / a.Wout;
+                const int oh = q % a.Hout;
+                const int n = q / a.Hout;
+                if (AMODE == A_STEM) {
+                    ih0[i] = oh * 2 - 3;
+                    iw0[i] = ow * 2 - 4;
+                    base[i] = (n * 8 + t) * a.Hin;
+                } else {
+                    ih0[i] = oh * a.stride - a.pad;
+                    iw0[i] = ow * a.stride - a.pad;
+                    base[i] = n * a.Hin;
+                }
+            }
+            int r = 0, s = 0, cb = 0;
+            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                const int slot = it % p.a_stages;
+                mbar_wait(&a_empty[slot], ((it / p.a_stages) & 1) ^ 1);
+                const uint32_t dst = dst_thread + slot * p.a_stage_bytes;
+                if (AMODE == A_STEM) {
+                    const int rr = 2 * kb + (j >> 2);
+                    const int dw = 2 * (j & 3);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ih = ih0[i] + rr;
+                        const int iw = iw0[i] + dw;
+                        const bool ok = rowok[i] && rr < 7 && (unsigned)ih < (unsigned)a.Hin && iw >= 0 && iw < a.Win;
+                        const size_t off = ok ? ((size_t)(base[i] + ih) * a.Win + iw) * 4 : 0;
+                        cp_async_16(dst + i * 2048, a.in + off, ok ? 16u : 0u);
+                    }
+                } else {
+                    const int c = cb * kTileK + j * 8;
+                    int tt = t;
+                    if (a.fold) tt += (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
+                    const bool tok = (unsigned)tt < 8u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ih = ih0[i] + r;
+                        const int iw = iw0[i] + s;
+                        const bool ok =
+                            rowok[i] && tok && (unsigned)ih < (unsigned)a.Hin && (unsigned)iw < (unsigned)a.Win;
+                        const size_t off = ok ? (((size_t)(base[i] + ih) * a.Win + iw) * 8 + tt) * a.Cin + c : 0;
+                        cp_async_16(dst + i * 2048, a.in + off, ok ? 16u : 0u);
+                    }
+                    if (++cb == a.cin_blocks) {
+                        cb = 0;
+                        if (++s == a.S) {
+                            s = 0;
+                            ++r;
+                        }
+                    }
+                }
+                cp_async_mbar_arrive_noinc(&a_full[slot]);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+}  // namespace wd

@@ -18,6 +18,7 @@
 #include "wd_conv_persistent.cuh"
 #include "wd_conv_umma.cuh"
 #include "wd_conv_v3.cuh"
+#include "wd_conv_v4.cuh"
 
 namespace {
 
@@ -137,7 +138,7 @@ struct wd_engine {
     bool weights_loaded = false;
     int use_tma_a = 1;
     int tile_n_max = 256;
-    int persistent = 2;  // 0: one tile per CTA, 1: persistent v2, 2: persistent v3 (W-resident, strip 3x3)
+    int persistent = 3;  // 0: one tile per CTA, 1: persistent v2, 2: v3 (W-resident, strip 3x3), 3: v4 (uniform MMA issue)
     int use_strip = 1;
     int sm_count = 148;
     std::vector<ConvLayer> convs;
@@ -341,7 +342,7 @@ int plan_smem(int BN, int mode, int kblocks, bool has_res, bool grid_keeps_n_til
     const int a_stage = strip ? wd::kStripStage : wd::kATileBytes;
     const int out_b = 8 * wd::kEpiSlab;
     const int res_b = has_res ? 4 * wd::kResDepth * wd::kEpiSlab : 0;
-    const int bars = 1024;
+    const int bars = 2048;  // mbarriers + TMEM pointer (512 B) + the n-tile's bias (v4: up to 256 floats)
     const int avail = kMaxDynamic - 1024 - out_b - res_b - bars;
     SmemPlan p{};
     p.a_stage_bytes = a_stage;
@@ -422,6 +423,66 @@ int launch_v3(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
     return fail(WD_ERR_INVALID, "no v3 conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
 }
 
+
+template <int BN, int AMODE, bool RES>
+int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_v4_kernel<BN, AMODE, RES>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::ConvArgs3 p{};
+    p.c = a;
+    int grid = std::min(a.num_tiles, sm_count);
+    grid = std::max(a.n_tiles, (grid / a.n_tiles) * a.n_tiles);  // a CTA keeps one n-tile (bias + resident W)
+    SmemPlan sp;
+    WD_TRY(plan_smem(BN, AMODE, a.kblocks, RES, true, &sp));
+    p.a_stages = sp.a_stages;
+    p.b_stages = sp.b_stages;
+    p.w_resident = sp.w_resident;
+    p.a_stage_bytes = sp.a_stage_bytes;
+    p.off_b = sp.off_b;
+    p.off_out = sp.off_out;
+    p.off_res = sp.off_res;
+    p.off_bar = sp.off_bar;
+    p.tiles_w = AMODE == wd::A_STRIP ? a.Wout / wd::kStripPixels : 1;
+    const unsigned threads = (AMODE == wd::A_TMA || AMODE == wd::A_STRIP) ? 224 : 320;
+    kfn<<<(unsigned)grid, threads, sp.total, st>>>(c.wmap, c.amap, c.omap, c.rmap, c.omap16, p);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+template <int BN>
+int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    const bool res = a.residual != nullptr;
+    switch (c.a_mode) {
+        case wd::A_STEM:
+            if (BN == 64 && !res) return launch_v4_t<64, wd::A_STEM, false>(c, a, sm_count, st);
+            break;
+        case wd::A_TMA:
+            return res ? launch_v4_t<BN, wd::A_TMA, true>(c, a, sm_count, st)
+                       : launch_v4_t<BN, wd::A_TMA, false>(c, a, sm_count, st);
+        case wd::A_STRIP:
+            if (!res) return launch_v4_t<BN, wd::A_STRIP, false>(c, a, sm_count, st);
+            break;
+        case wd::A_GATHER:
+            return res ? launch_v4_t<BN, wd::A_GATHER, true>(c, a, sm_count, st)
+                       : launch_v4_t<BN, wd::A_GATHER, false>(c, a, sm_count, st);
+    }
+    return fail(WD_ERR_INVALID, "no v4 conv kernel for tile_n=%d a_mode=%d residual=%d", c.tile_n, c.a_mode, (int)res);
+}
+
+int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    if (c.a_mode == wd::A_STRIP) a.num_tiles = (a.M / wd::kStripRows) * a.n_tiles;  // tiles are 14-pixel row segments
+    switch (c.tile_n) {
+        case 64: return launch_v4_bn<64>(c, a, sm_count, st);
+        case 128: return launch_v4_bn<128>(c, a, sm_count, st);
+        case 256: return launch_v4_bn<256>(c, a, sm_count, st);
+    }
+    return fail(WD_ERR_INVALID, "no v4 conv kernel for tile_n=%d", c.tile_n);
+}
+
 int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st);
 
 int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
@@ -444,8 +505,9 @@ int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
 }
 
 int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st) {
-    if (version >= 2) return launch_v3(c, a, sm_count, st);
-    if (c.a_mode == wd::A_STRIP) return fail(WD_ERR_INVALID, "strip mode needs the v3 kernel");
+    if (version >= 3) return launch_v4(c, a, sm_count, st);
+    if (version == 2) return launch_v3(c, a, sm_count, st);
+    if (c.a_mode == wd::A_STRIP) return fail(WD_ERR_INVALID, "strip mode needs the v3/v4 kernel");
     if (version == 1) return launch_persist(c, a, sm_count, st);
     return launch_conv(c, a, st);
 }
@@ -792,7 +854,7 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     if (!strcmp(key, "use_tma_a")) {
         e->use_tma_a = value ? 1 : 0;
     } else if (!strcmp(key, "persistent")) {
-        if (value < 0 || value > 2) return fail(WD_ERR_INVALID, "persistent must be 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
     } else if (!strcmp(key, "use_strip")) {
         e->use_strip = value ? 1 : 0;

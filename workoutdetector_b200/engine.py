@@ -203,7 +203,7 @@ def scores_to_states(scores: torch.Tensor, threshold: float = 0.5, softmax: bool
 
 
 def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor], stride: int,
-               fold: int, relu: bool, a_mode: str, tile_n: int, persistent: int = 2) -> torch.Tensor:
+               fold: int, relu: bool, a_mode: str, tile_n: int, persistent: int = 3) -> torch.Tensor:
     """Test hook: one tcgen05 conv. x bf16 cuda [clips,H,W,8,Cin] (T-inner); w fp32 [Cout,Cin,k,k]."""
     lib = _lib.load()
     clips, Hin, Win, T, Cin = x.shape
@@ -221,7 +221,7 @@ def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: O
 
 
 def bench_conv(clips: int, H: int, Cin: int, Cout: int, k: int, stride: int, fold: int, residual: bool, a_mode: str,
-               tile_n: int, persistent: int = 2, iters: int = 20) -> float:
+               tile_n: int, persistent: int = 3, iters: int = 20) -> float:
     """Measurement hook: milliseconds per launch of one conv layer shape on random data (CUDA events)."""
     lib = _lib.load()
     x = torch.randn(clips, H, H, 8, Cin, device="cuda").to(torch.bfloat16)
