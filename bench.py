@@ -232,8 +232,8 @@ def main():
         *_, op_ms = eng.forward(frames, timed=True)
         acc = [a + m for a, m in zip(acc, op_ms)]
     op_ms = [a / timed_iters for a in acc]
-    conv_ms = sum(m for m, o in zip(op_ms, ops) if o["kind"] in ("conv", "stem"))
-    conv_flops = sum(2.0 * o["macs_per_clip"] * B for o in ops if o["kind"] in ("conv", "stem"))
+    conv_ms = sum(m for m, o in zip(op_ms, ops) if o["kind"] in ("conv", "stem", "stem_pool"))
+    conv_flops = sum(2.0 * o["macs_per_clip"] * B for o in ops if o["kind"] in ("conv", "stem", "stem_pool"))
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")   # dram bytes per step from the ncu --set full capture
@@ -242,7 +242,7 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_step")
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["sustained"], traffic=traffic,
-                    kernel="conv_umma_kernel (53 launches per step, aggregated)",
+                    kernel="conv_v4_kernel x52 + stem_pool_kernel (all tcgen05 launches of a step, aggregated)",
                     frac_of_burst=achieved / peaks["burst"], peak_source=peaks["source"],
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / max(sum(op_ms), 1e-9),
                     whole_step_tflops=value / world * GFLOP_PER_CLIP / 1e3,

@@ -75,25 +75,30 @@ int wd_engine_destroy(wd_engine* e);
  * descriptors.  Synchronous.  Tensors named "*.num_batches_tracked" and unknown names are ignored. */
 int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* tensors, int n);
 
-/* Size in bytes of one preprocessed frame ([224,224,4] in the engine's element type: bf16 or fp32). */
+/* Engine frames.  BF16 mode: bf16 [224, 240, 4] per frame — the image sits at columns 8..231, the 8 columns on each
+ * side and channel 3 are zero (the fused stem reads 8-pixel filter windows through a sliding-window TMA view and never
+ * checks horizontal bounds).  FP32_VALIDATE mode: fp32 [224, 224, 4].  wd_preprocess_u8 / wd_pack_nchw_f32 write this
+ * layout including the zero columns; wd_engine_frame_geometry reports it (height 224, row pitch in pixels, zero
+ * columns left of the image) and wd_engine_frame_bytes the size of one frame. */
 size_t wd_engine_frame_bytes(const wd_engine* e);
+int wd_engine_frame_geometry(const wd_engine* e, int32_t* height, int32_t* pitch, int32_t* pad_left);
 
 /* Replaces build_test_transform(person_crop=False) (datasets/build.py:131-136) plus the window gather of
  * inference_dataset (utils/inference_count.py:411-414).
  *   frames_hwc : device uint8 [n_src, H, W, 3]
  *   src_index  : device int32 [n_out] or NULL (identity, n_out == n_src); entry < 0 = all-zero raw frame
  *   in_scale   : 1/255 for uint8 semantics; 1.0 reproduces the float-promotion quirk of inference_count.py:413
- *   out_frames : device [n_out, 224, 224, 4] in the engine's element type */
+ *   out_frames : device [n_out] engine frames (layout above) */
 int wd_preprocess_u8(wd_engine* e, const uint8_t* frames_hwc, int n_src, int H, int W, const int32_t* src_index,
                      int n_out, float in_scale, void* out_frames, void* stream);
 
 /* Input adapter for callers that hold what the reference module takes (tsm.py:409): device fp32
- * [n_frames, 3, 224, 224], already normalised -> engine frames [n_frames, 224, 224, 4]. */
+ * [n_frames, 3, 224, 224], already normalised -> [n_frames] engine frames. */
 int wd_pack_nchw_f32(wd_engine* e, const float* x_nchw, int n_frames, void* out_frames, void* stream);
 
 /* Replaces TSM.forward (tsm.py:409-419) + to_softmax (utils/visualize.py:140-150) + the arg-max / threshold of
  * utils/eval.py:159-164.
- *   frames : device [n_clips*8, 224, 224, 4], frame index = clip*8 + segment
+ *   frames : device [n_clips*8] engine frames, frame index = clip*8 + segment
  *   logits : device fp32 [n_clips, num_class] (raw consensus scores, what the reference module returns)
  *   probs  : device fp32 [n_clips, num_class] or NULL
  *   state  : device int32 [n_clips] or NULL; arg-max class (first index on ties) if its score >= threshold
@@ -130,22 +135,24 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, 
 
 /* ---- introspection, tuning and test hooks (not part of the reference surface) ---- */
 int wd_engine_num_ops(const wd_engine* e);
-/* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head), Cin, Cout, ksize, stride, Hout, Wout, fold,
+/* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head, 4 fused stem conv + maxpool), Cin, Cout, ksize, stride, Hout, Wout, fold,
  *              a_mode (0 gather, 1 stem, 2 tma, 3 strip, -1 n/a), tile_n;   macs_per_clip = multiply-accumulates per clip */
 int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int32_t* info, double* macs_per_clip);
 /* After op `idx` runs in the next forwards, its output is converted to fp32 NCHW frames [n_clips*8, C, H, W]
  * at dst (device).  idx < 0 disables.  The head op (logits) cannot be tapped. */
 int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems);
-/* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (0: one tile per CTA, 1: persistent v2, 2: persistent v3 = default),
- * "use_strip" (0/1: row-strip A operand for 3x3 stride-1 convolutions, v3 only).  Takes effect at the next wd_engine_load_weights. */
+/* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (conv kernel generation: 0 one tile per CTA, 1 v2,
+ * 2 v3, 3 v4 = default), "use_strip" (0/1: row-strip A operand for 3x3 stride-1 convolutions, v3/v4),
+ * "stem_seg_rows" (pooled rows per work unit of the fused stem, divides 56).  Takes effect at the next
+ * wd_engine_load_weights. */
 int wd_engine_set_option(wd_engine* e, const char* key, int value);
 /* Number of kernels the engine launched since creation (all are this library's own kernels). */
 int64_t wd_engine_launch_count(const wd_engine* e);
 
 /* Run ONE convolution outside an engine (tests): x device bf16 T-inner [clips,Hin,Win,8,Cin], w host fp32
  * [Cout,Cin,k,k], bias host fp32 [Cout], residual device bf16 or NULL -> y device bf16 [clips,Hout,Wout,8,Cout].
- * a_mode: 0 gather, 2 TMA (1x1 stride 1 only), 3 strip (3x3 stride 1, W multiple of 14; persistent=2 only);
- * persistent selects the kernel generation (0, 1, 2).  Synchronous. */
+ * a_mode: 0 gather, 2 TMA (1x1 stride 1 only), 3 strip (3x3 stride 1, W multiple of 14; persistent >= 2);
+ * persistent selects the kernel generation (0..3).  Synchronous. */
 int wd_debug_conv(const void* x, const float* w, const float* bias, const void* residual, void* y, int clips,
                   int Hin, int Win, int Cin, int Cout, int ksize, int stride, int fold, int relu, int a_mode,
                   int tile_n, int persistent);

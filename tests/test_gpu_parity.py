@@ -155,9 +155,12 @@ def test_preprocess_vs_oracle(engines, hw):
         for mode, tol in (("fp32", 2e-6), ("bf16", 8e-3)):
             e = engines(mode, "init")
             out = e.preprocess_u8(fr.cuda(), idx.cuda(), in_scale=in_scale).float().cpu()
-            assert out.shape == (7, 224, 224, 4)
+            assert out.shape == (7,) + e.frame_shape
             assert float(out[..., 3].abs().max()) == 0.0
-            got = out[..., :3].permute(0, 3, 1, 2)
+            pad = e.frame_pad                                  # bf16 frames carry zero columns for the fused stem
+            assert float(out[:, :, :pad].abs().max() if pad else 0.0) == 0.0
+            assert float(out[:, :, pad + 224:].abs().max() if out.shape[2] > pad + 224 else 0.0) == 0.0
+            got = e.image_view(out).permute(0, 3, 1, 2)
             scale = float(ref.abs().max())
             assert float((got - ref).abs().max()) <= tol * max(1.0, scale), (mode, in_scale)
 
@@ -551,7 +554,7 @@ def test_abi_error_paths(weights):
                     max_clips=1, mode=0, device=0)
     assert lib.wd_engine_create(C.byref(bad), C.byref(h)) == -1 and b"num_segments" in lib.wd_last_error()
     e = Engine(12, max_clips=1)
-    fr = torch.zeros(8, 224, 224, 4, dtype=torch.bfloat16, device="cuda")
+    fr = torch.zeros((8,) + e.frame_shape, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(WdError, match="before wd_engine_load_weights"):
         e.forward(fr)
     sd = dict(weights["init"])
@@ -560,8 +563,8 @@ def test_abi_error_paths(weights):
         e.load_state_dict(sd)
     e.load_state_dict(weights["init"])
     with pytest.raises(WdError, match="max_clips"):
-        e.forward(torch.zeros(16, 224, 224, 4, dtype=torch.bfloat16, device="cuda"))
+        e.forward(torch.zeros((16,) + e.frame_shape, dtype=torch.bfloat16, device="cuda"))
     assert e.launch_count() == 0
     e.forward(fr)
-    assert e.launch_count() == len(e.ops())     # 53 convs + maxpool + head, all this library's kernels
+    assert e.launch_count() == len(e.ops())     # fused stem+maxpool, 52 convs, head: all this library's kernels
     e.close()

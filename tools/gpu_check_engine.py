@@ -54,7 +54,7 @@ def sec_aux():
             ref = O.preprocess_u8(fr)
             idx = torch.tensor([0, 2, 4, -1, 1, 3], dtype=torch.int32)
             out = eng.preprocess_u8(fr.cuda(), idx.cuda()).float().cpu()  # [6,224,224,4]
-            got = out[..., :3].permute(0, 3, 1, 2)
+            got = eng.image_view(out).permute(0, 3, 1, 2)
             refi = torch.stack([ref[i] if i >= 0 else O.preprocess_u8(torch.zeros(1, H, W_, 3, dtype=torch.uint8))[0]
                                 for i in idx.tolist()])
             err = float((got - refi).abs().max())

@@ -61,6 +61,7 @@ SYMBOLS = {
     "wd_engine_num_ops": (_i, [_vp]),
     "wd_engine_op_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "wd_engine_set_tap": (_i, [_vp, _i, _vp, C.c_int64]),
+    "wd_engine_frame_geometry": (_i, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "wd_engine_set_option": (_i, [_vp, C.c_char_p, _i]),
     "wd_engine_launch_count": (C.c_int64, [_vp]),
     "wd_debug_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),

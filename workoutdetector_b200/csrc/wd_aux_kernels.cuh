@@ -96,18 +96,21 @@ struct PreArgs {
     float scale_y, scale_x;  // H/rh, W/rw  (torch area_pixel_compute_scale, align_corners=False)
     float in_scale;          // 1/255 (uint8 semantics) or 1 (float-promotion quirk, inference_count.py:413)
     float mean[3], stdv[3];
+    int pitch, pad;          // output row pitch in pixels and zero columns left of the image (blockDim.x == pitch)
 };
 
 template <typename OutT>
-__global__ void __launch_bounds__(224) preprocess_u8_kernel(const PreArgs a, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const PreArgs a, OutT* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t srow[];
     const int oy = blockIdx.x;
     const int f = blockIdx.y;
-    const int ox = threadIdx.x;
+    const int ox = (int)threadIdx.x - a.pad;          // image column; outside [0, 224) = zero padding column
+    const bool inside = (unsigned)ox < 224u;
     const int src = a.src_index ? a.src_index[f] : f;
-    OutT* o = out + (((size_t)f * 224 + oy) * 224 + ox) * 4;
+    OutT* o = out + (((size_t)f * 224 + oy) * a.pitch + threadIdx.x) * 4;
+    if (!inside) Px4<OutT>::store(o, 0.0f, 0.0f, 0.0f);
     if (src < 0) {  // zero raw frame: (0*in_scale - mean) / std
-        Px4<OutT>::store(o, -a.mean[0] / a.stdv[0], -a.mean[1] / a.stdv[1], -a.mean[2] / a.stdv[2]);
+        if (inside) Px4<OutT>::store(o, -a.mean[0] / a.stdv[0], -a.mean[1] / a.stdv[1], -a.mean[2] / a.stdv[2]);
         return;
     }
     // vertical source coordinate (torch upsample_bilinear2d, align_corners=False)
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(224) preprocess_u8_kernel(const PreArgs a, Out
         *reinterpret_cast<uint4*>(srow + (size_t)v * 16) = val;
     }
     __syncthreads();
+    if (!inside) return;
 
     float sx = a.scale_x * ((float)(ox + a.left) + 0.5f) - 0.5f;
     sx = sx < 0.0f ? 0.0f : sx;
@@ -160,15 +164,23 @@ __global__ void __launch_bounds__(224) preprocess_u8_kernel(const PreArgs a, Out
     Px4<OutT>::store(o, res[0], res[1], res[2]);
 }
 
-// [F,3,H,W] float (already normalised, what the reference nn.Module takes: tsm.py:409) -> [F,H,W,4]
+// [F,3,224,224] float (already normalised, what the reference nn.Module takes: tsm.py:409) -> [F,224,pitch,4];
+// columns outside [pad, pad+224) are written as zeros.
 template <typename OutT>
-__global__ void pack_nchw_f32_kernel(const float* __restrict__ in, OutT* __restrict__ out, int F, int HW) {
+__global__ void pack_nchw_f32_kernel(const float* __restrict__ in, OutT* __restrict__ out, int F, int pitch, int pad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)F * HW) return;
-    const size_t f = i / HW;
-    const size_t p = i % HW;
-    const float* b = in + f * 3 * HW + p;
-    Px4<OutT>::store(out + i * 4, b[0], b[HW], b[2 * (size_t)HW]);
+    if (i >= (size_t)F * 224 * pitch) return;
+    const int x = (int)(i % pitch) - pad;
+    const size_t fy = i / pitch;
+    const size_t f = fy / 224;
+    const int y = (int)(fy % 224);
+    if ((unsigned)x >= 224u) {
+        Px4<OutT>::store(out + i * 4, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    const size_t HW = 224 * 224;
+    const float* b = in + f * 3 * HW + (size_t)y * 224 + x;
+    Px4<OutT>::store(out + i * 4, b[0], b[HW], b[2 * HW]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@
 #include "wd_conv_umma.cuh"
 #include "wd_conv_v3.cuh"
 #include "wd_conv_v4.cuh"
+#include "wd_stem_pool.cuh"
 
 namespace {
 
@@ -68,7 +69,7 @@ int get_encode_fn(EncodeTiledFn* out) {
 
 // bf16 tensor map, 128-byte swizzle. dims/strides innermost first; strides in bytes for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                   const uint32_t* box) {
+                   const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn;
     WD_TRY(get_encode_fn(&fn));
     cuuint64_t gdim[5], gstr[5];
@@ -80,8 +81,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
         if (i > 0) gstr[i - 1] = strides[i - 1];
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                    bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(WD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return WD_OK;
 }
@@ -97,7 +98,7 @@ inline uint16_t f32_to_bf16_bits(float f) {  // round-to-nearest-even, as __floa
 // ---------------------------------------------------------------------------------------------------
 // Plan
 // ---------------------------------------------------------------------------------------------------
-enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_MAXPOOL = 2, OP_HEAD = 3 };
+enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_MAXPOOL = 2, OP_HEAD = 3, OP_STEMPOOL = 4 };
 
 struct ConvLayer {
     std::string name;      // e.g. "layer1.0.conv1"
@@ -140,6 +141,7 @@ struct wd_engine {
     int tile_n_max = 256;
     int persistent = 3;  // 0: one tile per CTA, 1: persistent v2, 2: v3 (W-resident, strip 3x3), 3: v4 (uniform MMA issue)
     int use_strip = 1;
+    int stem_seg_rows = 28;  // pooled rows per work unit of the fused stem + max-pool kernel
     int sm_count = 148;
     std::vector<ConvLayer> convs;
     std::vector<Op> ops;
@@ -211,8 +213,22 @@ int build_plan(wd_engine* e) {
     const int H0 = e->desc.height;
     int ci = add_conv("conv1", "base_model.conv1.weight", "", "base_model.bn1", 3, 64, 7, 2, H0, 0, 1);
     e->convs[ci].stem = true;
-    add_conv_op(ci, -1, 0, -1);
-    {
+    if (e->desc.mode == WD_MODE_BF16) {
+        // conv1 + bn1 + relu + maxpool are ONE kernel (wd_stem_pool.cuh); the 112x112x64 activation never exists
+        Op o;
+        o.kind = OP_STEMPOOL;
+        o.conv = ci;
+        o.in_buf = -1;
+        o.out_buf = 1;
+        o.name = "maxpool";
+        o.C = 64;
+        o.H = o.W = e->convs[ci].Hout / 2;
+        o.macs_per_clip = 8.0 * 112 * 112 * 64.0 * 3 * 49;
+        e->ops.push_back(o);
+    } else {
+        add_conv_op(ci, -1, 0, -1);
+    }
+    if (e->desc.mode != WD_MODE_BF16) {
         Op o;
         o.kind = OP_MAXPOOL;
         o.in_buf = 0;
@@ -565,20 +581,16 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     int Kp;
     std::vector<uint16_t> p;
     if (c.stem) {
-        // k-block kb, chunk j (8 elements = 2 pixels x 4 ch): r = 2*kb + (j>>2), s = 2*(j&3) + px - 1
-        Kp = 256;
+        // K = 7 filter rows x 32: k = r*32 + slot*4 + ch, slot j is tap s = j-1 (slot 0 and ch 3 are zero)
+        Kp = 224;
         p.assign((size_t)c.Cout * Kp, 0);
         for (int co = 0; co < c.Cout; ++co)
-            for (int kb = 0; kb < 4; ++kb)
-                for (int j = 0; j < 8; ++j)
-                    for (int px = 0; px < 2; ++px)
-                        for (int ch = 0; ch < 3; ++ch) {
-                            const int r = 2 * kb + (j >> 2);
-                            const int s = 2 * (j & 3) + px - 1;
-                            if (r >= 7 || s < 0 || s >= 7) continue;
-                            const float v = w[(((size_t)co * 3 + ch) * 7 + r) * 7 + s] * scale[co];
-                            p[(size_t)co * Kp + kb * 64 + j * 8 + px * 4 + ch] = f32_to_bf16_bits(v);
-                        }
+            for (int r = 0; r < 7; ++r)
+                for (int s = 0; s < 7; ++s)
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float v = w[(((size_t)co * 3 + ch) * 7 + r) * 7 + s] * scale[co];
+                        p[(size_t)co * Kp + r * 32 + (s + 1) * 4 + ch] = f32_to_bf16_bits(v);
+                    }
     } else {
         if (c.Cin % 64 != 0) return fail(WD_ERR_INVALID, "%s: Cin=%d is not a multiple of 64", c.name.c_str(), c.Cin);
         Kp = K;
@@ -591,7 +603,7 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
                         p[(size_t)co * Kp + (size_t)(r * c.k + s) * c.Cin + ci] = f32_to_bf16_bits(v);
                     }
     }
-    c.kblocks = Kp / 64;
+    c.kblocks = c.stem ? 7 : Kp / 64;
     c.tile_n = std::min(c.Cout, tile_n_max);
     if (c.stem) c.tile_n = 64;
     if (c.Cout % c.tile_n != 0)
@@ -608,6 +620,11 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     WD_CUDA(cudaMemcpy(c.w_packed, p.data(), p.size() * 2, cudaMemcpyHostToDevice));
     const uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)c.Cout};
     const uint64_t strides[1] = {(uint64_t)Kp * 2};
+    if (c.stem) {  // 64-byte rows, SWIZZLE_64B: one box per filter row
+        const uint32_t box[2] = {32, 64};
+        WD_TRY(make_tmap_bf16(&c.wmap, c.w_packed, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
+        return WD_OK;
+    }
     const uint32_t box[2] = {64, (uint32_t)c.tile_n};
     WD_TRY(make_tmap_bf16(&c.wmap, c.w_packed, 2, dims, strides, box));
     return WD_OK;
@@ -638,6 +655,33 @@ int make_amap(CUtensorMap* map, const void* base, int Cin, size_t pixels) {
     return make_tmap_bf16(map, base, 3, dims, strides, box);
 }
 
+// Fused stem: 5-D sliding-window view of the padded frames {32 el, 224 rows, 8 t, 114 conv columns, clips}; the conv
+// column dimension has a 16-byte stride (2 pixels), coordinate c+1 for conv column c (wd_stem_pool.cuh).
+int launch_stem_pool(wd_engine* e, const ConvLayer& c, const void* frames, void* out, int n_clips, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(wd::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::kSpSmem));
+        configured = true;
+    }
+    const uint64_t row = (uint64_t)wd::kFramePitch * 8, frame = 224 * row;
+    const uint64_t dims[5] = {32, 224, 8, 114, (uint64_t)n_clips};
+    const uint64_t strides[4] = {row, frame, 16, 8 * frame};
+    const uint32_t box[5] = {32, 1, 8, 16, 1};
+    CUtensorMap amap;
+    WD_TRY(make_tmap_bf16(&amap, static_cast<const uint8_t*>(frames) + 16, 5, dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_64B));
+    wd::StemPoolArgs p{};
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.bias = c.bias;
+    p.clips = n_clips;
+    p.seg_rows = e->stem_seg_rows;
+    p.num_units = n_clips * (56 / p.seg_rows) * 8;
+    const int grid = std::min(p.num_units, e->sm_count);
+    wd::stem_pool_kernel<<<grid, 192, wd::kSpSmem, st>>>(amap, c.wmap, p);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, float* probs, int32_t* state,
                 float threshold, int apply_softmax, cudaStream_t st, float* op_ms) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
@@ -658,7 +702,10 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
         const void* in = o.in_buf < 0 ? frames : e->buf[o.in_buf];
         void* out = o.out_buf < 0 ? nullptr : e->buf[o.out_buf];
         const void* res = o.res_buf < 0 ? nullptr : e->buf[o.res_buf];
-        if (o.kind == OP_STEM || o.kind == OP_CONV) {
+        if (o.kind == OP_STEMPOOL) {
+            WD_TRY(launch_stem_pool(e, e->convs[o.conv], frames, out, n_clips, st));
+            ++e->launches;
+        } else if (o.kind == OP_STEM || o.kind == OP_CONV) {
             const ConvLayer& c = e->convs[o.conv];
             if (f32) {
                 wd::ConvF32Args a{};
@@ -769,10 +816,15 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     const size_t smem = (size_t)2 * W * 3 + 48;
     if (smem > 48 * 1024) return fail(WD_ERR_INVALID, "frame width %d too large for the row staging buffer", W);
     dim3 grid(224, n_out);
-    if (mode == WD_MODE_FP32_VALIDATE)
+    if (mode == WD_MODE_FP32_VALIDATE) {
+        a.pitch = 224;
+        a.pad = 0;
         wd::preprocess_u8_kernel<float><<<grid, 224, smem, st>>>(a, static_cast<float*>(out));
-    else
-        wd::preprocess_u8_kernel<__nv_bfloat16><<<grid, 224, smem, st>>>(a, static_cast<__nv_bfloat16*>(out));
+    } else {  // padded frames for the fused stem: image at columns kFramePad .. kFramePad+223, zeros around it
+        a.pitch = wd::kFramePitch;
+        a.pad = wd::kFramePad;
+        wd::preprocess_u8_kernel<__nv_bfloat16><<<grid, wd::kFramePitch, smem, st>>>(a, static_cast<__nv_bfloat16*>(out));
+    }
     WD_CUDA(cudaGetLastError());
     return WD_OK;
 }
@@ -856,6 +908,9 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     } else if (!strcmp(key, "persistent")) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
+    } else if (!strcmp(key, "stem_seg_rows")) {
+        if (value < 1 || 56 % value != 0) return fail(WD_ERR_INVALID, "stem_seg_rows must divide 56");
+        e->stem_seg_rows = value;
     } else if (!strcmp(key, "use_strip")) {
         e->use_strip = value ? 1 : 0;
     } else if (!strcmp(key, "tile_n_max")) {
@@ -931,7 +986,20 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     return WD_OK;
 }
 
-size_t wd_engine_frame_bytes(const wd_engine* e) { return e ? (size_t)224 * 224 * 4 * e->elem_size : 0; }
+size_t wd_engine_frame_bytes(const wd_engine* e) {
+    if (!e) return 0;
+    const int pitch = e->desc.mode == WD_MODE_BF16 ? wd::kFramePitch : 224;
+    return (size_t)224 * pitch * 4 * e->elem_size;
+}
+
+int wd_engine_frame_geometry(const wd_engine* e, int32_t* height, int32_t* pitch, int32_t* pad_left) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    const bool bf = e->desc.mode == WD_MODE_BF16;
+    if (height) *height = 224;
+    if (pitch) *pitch = bf ? wd::kFramePitch : 224;
+    if (pad_left) *pad_left = bf ? wd::kFramePad : 0;
+    return WD_OK;
+}
 
 int wd_preprocess_u8(wd_engine* e, const uint8_t* frames, int n_src, int H, int W, const int32_t* src_index,
                      int n_out, float in_scale, void* out, void* stream) {
@@ -946,14 +1014,15 @@ int wd_pack_nchw_f32(wd_engine* e, const float* x, int n_frames, void* out, void
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
     if (n_frames == 0) return WD_OK;
     if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
-    const int HW = 224 * 224;
-    const size_t total = (size_t)n_frames * HW;
+    const bool bf = e->desc.mode == WD_MODE_BF16;
+    const int pitch = bf ? wd::kFramePitch : 224, pad = bf ? wd::kFramePad : 0;
+    const size_t total = (size_t)n_frames * 224 * pitch;
     const unsigned grid = (unsigned)((total + 255) / 256);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (e->desc.mode == WD_MODE_FP32_VALIDATE)
-        wd::pack_nchw_f32_kernel<float><<<grid, 256, 0, st>>>(x, static_cast<float*>(out), n_frames, HW);
+    if (!bf)
+        wd::pack_nchw_f32_kernel<float><<<grid, 256, 0, st>>>(x, static_cast<float*>(out), n_frames, pitch, pad);
     else
-        wd::pack_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), n_frames, HW);
+        wd::pack_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), n_frames, pitch, pad);
     WD_CUDA(cudaGetLastError());
     ++e->launches;
     return WD_OK;

@@ -1,0 +1,280 @@
+// wd_stem_pool.cuh — the TSM-R50 stem as ONE kernel: conv 7x7/2 (3->64) + folded BN + ReLU + max-pool 3x3/2 (sm_100a).
+//
+// Replaces torchvision ResNet.conv1 / bn1 / relu / maxpool as used by the reference (workoutdetector/models/tsm.py:268,
+// torchvision resnet.py `_forward_impl`).  The 112x112x64 stem activation (1.6 MB per frame in bf16) is never
+// written to HBM: a CTA walks down a strip of 15 conv columns, keeps the last four ReLU'd conv rows in shared memory
+// and emits one pooled row (7 pooled columns x 8 segments x 64 channels = 7 KiB, contiguous in the T-inner layout)
+// for every second conv row.  HBM traffic per frame drops from 0.4 (in) + 1.6 (stem out) + 1.6 (pool in) + 0.4 MB
+// to 0.43 + 0.4 MB.
+//
+// Input frames: bf16 [F, 224, kFramePitch=240, 4] — the image sits at columns 8..231, the 8 columns on each side and
+// channel 3 are zero (written by the preprocess kernel), so a filter window never needs a horizontal bounds check.
+//
+// GEMM view (per conv row of a strip): D[m, co] = sum_{r<7} sum_{k<32} A_r[m, k] * W_r[co, k]
+//   m = ow_local*8 + t  (16 conv columns x 8 segments = 128 rows; 15 columns are used)
+//   k = slot*4 + ch     (8 pixel slots x 4 channels of filter row r; slot j is tap s = j-1, slot 0 and ch 3 have zero
+//                        weights), 32 bf16 = 64 B per row -> SWIZZLE_64B K-major operands, two K=16 MMAs per filter row.
+//   A_r is ONE TMA box {32 el, 1 row, 8 t, 16 ow} of a 5-D view of the frames whose `ow` dimension has a 16-byte
+//   stride (two pixels): the windows of neighbouring conv columns overlap in memory, the box lands in shared memory
+//   as the ready 128 x 64 B operand.  Vertical padding is TMA's out-of-bounds fill (row coordinate < 0 or > 223).
+//   Input rows live in a ring of row PAIRS (2q, 2q+1): conv row oh reads rows 2oh-3 .. 2oh+3 = pairs oh-2 .. oh+1, so
+//   each conv row loads one new pair (16 KiB) and retires one: L2->SM traffic is 1x the input, not 3.5x.
+//
+// Warp roles (192 threads): 0-3 epilogue + pooling, 4 TMA producer, 5 MMA issuer + TMEM owner.
+#pragma once
+#include "wd_conv_v4.cuh"
+
+namespace wd {
+
+constexpr int kFramePitch = 240;  // pixels per padded frame row (bf16 engine frames)
+constexpr int kFramePad = 8;      // zero columns left of the image
+
+constexpr int kSpPairs = 6;                 // ring of input-row pairs
+constexpr int kSpBox = 128 * 64;            // one TMA box: 128 rows x 64 B
+constexpr int kSpPairBytes = 2 * kSpBox;    // 16 KiB
+constexpr int kSpWBytes = 7 * 64 * 64;      // 7 filter rows x [64 co x 64 B]
+constexpr int kSpRowSlots = 4;              // ReLU'd conv rows kept for pooling
+constexpr int kSpRowBytes = 128 * 128;      // 128 rows x 64 ch bf16
+constexpr int kSpOffW = kSpPairs * kSpPairBytes;
+constexpr int kSpOffRows = kSpOffW + kSpWBytes;
+constexpr int kSpOffBar = kSpOffRows + kSpRowSlots * kSpRowBytes;
+constexpr int kSpSmem = kSpOffBar + 512 + 1024;  // + barriers/bias + alignment slack
+
+struct StemPoolArgs {
+    __nv_bfloat16* out;  // [clips, 56, 56, 8, 64] T-inner
+    const float* bias;   // [64] folded BN shift
+    int clips;
+    int seg_rows;  // pooled rows per work unit (divides 56)
+    int num_units;  // clips * (56 / seg_rows) * 8 strips
+};
+
+// K-major SWIZZLE_64B descriptor: 8-row groups are 512 B apart.
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t umma_desc64_from_lo(uint32_t lo) {
+    return (static_cast<uint64_t>(kDescHiSw64) << 32) | lo;
+}
+
+__global__ void __launch_bounds__(192, 1)
+stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
+                 const StemPoolArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + kSpOffW;
+    uint8_t* sRows = smem + kSpOffRows;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSpOffBar);
+    uint64_t* full = bars;                 // [kSpPairs]
+    uint64_t* empty = bars + 8;            // [kSpPairs]
+    uint64_t* tmem_full_bar = bars + 16;   // [2]
+    uint64_t* tmem_empty_bar = bars + 18;  // [2]
+    uint64_t* w_bar = bars + 20;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+    float* sBias = reinterpret_cast<float*>(bars + 24);  // 64 floats
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const int nseg = 56 / p.seg_rows;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&amap);
+            tma_prefetch_desc(&wmap);
+            for (int s = 0; s < kSpPairs; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            mbar_init(w_bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_ptr, 128);
+        tmem_relinquish();
+    }
+    if (tid < 64) sBias[tid] = p.bias[tid];
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // unit -> (clip, first pooled row, strip); strips of one row band are neighbours so they share input rows in L2
+    auto decode = [&](int u, int& clip, int& ph0, int& strip) {
+        strip = u & 7;
+        const int v = u >> 3;
+        ph0 = (v % nseg) * p.seg_rows;
+        clip = v / nseg;
+    };
+
+    if (warp < 4) {
+        // ==========================================================================================
+        // Epilogue + pooling (128 threads)
+        // ==========================================================================================
+        const int m = warp * 32 + lane;  // tile row = TMEM lane: ow_local = m >> 3, t = m & 7
+        const uint32_t sw = m & 7;
+        int tile_iter = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int clip, ph0, strip;
+            decode(u, clip, ph0, strip);
+            const int oh_lo = max(0, 2 * ph0 - 1);
+            const int oh_hi = 2 * (ph0 + p.seg_rows) - 1;
+            const bool zero_row = (strip == 0 && m < 8);  // conv column -1 is pool padding
+            for (int oh = oh_lo; oh <= oh_hi; ++oh, ++tile_iter) {
+                const int acc = tile_iter & 1;
+                mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * 64;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                __syncwarp();
+                uint8_t* rowbuf = sRows + (oh & (kSpRowSlots - 1)) * kSpRowBytes + m * 128;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const uint32_t* v = (c8 < 4) ? (v0 + c8 * 8) : (v1 + (c8 - 4) * 8);
+                    const float4 b0 = *reinterpret_cast<const float4*>(sBias + c8 * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sBias + c8 * 8 + 4);
+                    uint4 o;
+                    o.x = pack_bf16x2_relu(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y);
+                    o.y = pack_bf16x2_relu(__uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);
+                    o.z = pack_bf16x2_relu(__uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y);
+                    o.w = pack_bf16x2_relu(__uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w);
+                    if (zero_row) o = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(rowbuf + ((c8 ^ sw) << 4)) = o;
+                }
+                // all four warps have written conv row oh (and finished pooling the previous rows)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int ph = (oh - 1) >> 1;
+                if ((oh & 1) && ph >= ph0) {
+                    // pooled row ph = max over conv rows 2ph-1 .. 2ph+1 (= oh-2 .. oh) and local columns 2j .. 2j+2
+                    const int r_first = (oh - 2 < 0) ? oh - 1 : oh - 2;
+                    __nv_bfloat16* orow =
+                        p.out + ((((size_t)clip * 56 + ph) * 56 + strip * 7) * 8) * 64;  // 7*8*64 contiguous elements
+                    for (int idx = tid; idx < 7 * 64; idx += 128) {
+                        const int j = idx >> 6;
+                        const int t = (idx >> 3) & 7;
+                        const int cv = idx & 7;
+                        __nv_bfloat162 best[4];
+                        bool first = true;
+                        for (int r = r_first; r <= oh; ++r) {
+                            const uint8_t* rb = sRows + (r & (kSpRowSlots - 1)) * kSpRowBytes;
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const int mm = (2 * j + dx) * 8 + t;
+                                const uint4 q = *reinterpret_cast<const uint4*>(rb + mm * 128 + ((cv ^ (mm & 7)) << 4));
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+                                if (first) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) best[e] = h[e];
+                                    first = false;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) best[e] = __hmax2(best[e], h[e]);
+                                }
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(orow + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(best);
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ==========================================================================================
+        // TMA producer: the 28 KiB of weights once, then one pair of input rows per conv row
+        // ==========================================================================================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(w_bar, kSpWBytes);
+            for (int r = 0; r < 7; ++r) tma_load_2d(&wmap, w_bar, sW + r * 4096, r * 32, 0);
+        }
+        __syncwarp();
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int clip, ph0, strip;
+            decode(u, clip, ph0, strip);
+            const int oh_lo = max(0, 2 * ph0 - 1);
+            const int oh_hi = 2 * (ph0 + p.seg_rows) - 1;
+            for (int q = oh_lo - 2; q <= oh_hi + 1; ++q, ++it) {
+                const int slot = it % kSpPairs;
+                mbar_wait(&empty[slot], ((it / kSpPairs) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[slot], kSpPairBytes);
+                    uint8_t* dst = sA + slot * kSpPairBytes;
+                    tma_load_5d(&amap, &full[slot], dst, 0, 2 * q, 0, strip * 14, clip);
+                    tma_load_5d(&amap, &full[slot], dst + kSpBox, 0, 2 * q + 1, 0, strip * 14, clip);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ==========================================================================================
+        // MMA issuer (warp 5): 14 x (M=128, N=64, K=16) per conv row
+        // ==========================================================================================
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+        const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
+        const uint32_t sW_lo = umma_desc_lo(smem_u32(sW));
+        mbar_wait(w_bar, 0);
+        uint32_t it_base = 0;  // running pair counter at the start of the unit (mirrors the producer's `it`)
+        int tile_iter = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int clip, ph0, strip;
+            decode(u, clip, ph0, strip);
+            const int oh_lo = max(0, 2 * ph0 - 1);
+            const int oh_hi = 2 * (ph0 + p.seg_rows) - 1;
+            const int q_lo = oh_lo - 2;
+            // the first conv row of the unit needs pairs q_lo .. q_lo+3; afterwards one new pair per row
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t i2 = it_base + k;
+                mbar_wait(&full[i2 % kSpPairs], (i2 / kSpPairs) & 1);
+            }
+            for (int oh = oh_lo; oh <= oh_hi; ++oh, ++tile_iter) {
+                const int acc = tile_iter & 1;
+                {
+                    const uint32_t i2 = it_base + (uint32_t)(oh + 1 - q_lo);  // pair oh+1
+                    mbar_wait(&full[i2 % kSpPairs], (i2 / kSpPairs) & 1);
+                }
+                mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * 64;
+                const uint32_t i_old = it_base + (uint32_t)(oh - 2 - q_lo);  // pair oh-2: retired by this row
+                const bool last = (oh == oh_hi);
+                if (elect_one()) {
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        const int row = 2 * oh - 3 + r;          // input row; pair = floor(row / 2)
+                        const int q = (row + 8) / 2 - 4;         // floor division for row >= -8
+                        const int j = row - 2 * q;
+                        const uint32_t i2 = it_base + (uint32_t)(q - q_lo);
+                        const uint32_t a_lo = sA_lo + (((i2 % kSpPairs) * kSpPairBytes + j * kSpBox) >> 4);
+                        const uint32_t b_lo = sW_lo + ((r * 4096) >> 4);
+                        umma_bf16_ss(d_tmem, umma_desc64_from_lo(a_lo), umma_desc64_from_lo(b_lo), idesc, r != 0 ? 1u : 0u);
+                        umma_bf16_ss(d_tmem, umma_desc64_from_lo(a_lo + 2), umma_desc64_from_lo(b_lo + 2), idesc, 1u);
+                    }
+                    umma_commit(&empty[i_old % kSpPairs]);
+                    if (last) {  // the unit is done: retire its last three pairs as well
+                        umma_commit(&empty[(i_old + 1) % kSpPairs]);
+                        umma_commit(&empty[(i_old + 2) % kSpPairs]);
+                        umma_commit(&empty[(i_old + 3) % kSpPairs]);
+                    }
+                    umma_commit(&tmem_full_bar[acc]);
+                }
+                __syncwarp();
+            }
+            it_base += (uint32_t)(oh_hi - oh_lo + 4);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace wd

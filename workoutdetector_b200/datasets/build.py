@@ -36,7 +36,7 @@ class B200TestTransform:
             x, scale = xr.to(torch.uint8), 1.0
         hwc = x.to(eng.device).permute(0, 2, 3, 1).contiguous()
         out = eng.preprocess_u8(hwc, None, in_scale=scale)          # [T,224,224,4] fp32
-        return out[..., :3].permute(0, 3, 1, 2).contiguous()
+        return eng.image_view(out).permute(0, 3, 1, 2).contiguous()
 
     def __repr__(self):
         return "B200TestTransform(ConvertImageDtype(float32), Resize(256), CenterCrop(224), Normalize(ImageNet))"

@@ -7,7 +7,7 @@ import torch
 from . import _lib
 from ._lib import MODE_BF16, MODE_FP32_VALIDATE, ModelDesc, NamedTensor, check
 
-OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head"}
+OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head", 4: "stem_pool"}
 A_MODES = {0: "gather", 1: "stem", 2: "tma", 3: "strip", -1: "-"}
 
 
@@ -40,6 +40,11 @@ class Engine:
         h = C.c_void_p()
         check(self.lib.wd_engine_create(C.byref(desc), C.byref(h)))
         self.h = h
+        fh, fp, fl = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.lib.wd_engine_frame_geometry(self.h, C.byref(fh), C.byref(fp), C.byref(fl)))
+        # engine frames: [224, pitch, 4]; the image is columns pad .. pad+223, the rest is zero (include/wd_b200.h)
+        self.frame_shape = (fh.value, fp.value, 4)
+        self.frame_pad = fl.value
         if use_tma_a is not None:
             self.set_option("use_tma_a", int(use_tma_a))
         if tile_n_max is not None:
@@ -107,7 +112,8 @@ class Engine:
 
     def preprocess_u8(self, frames: torch.Tensor, src_index: Optional[torch.Tensor] = None,
                       in_scale: float = 1.0 / 255.0) -> torch.Tensor:
-        """frames: cuda uint8 [n,H,W,3] -> [n_out,224,224,4] (datasets/build.py:131-136 semantics)."""
+        """frames: cuda uint8 [n,H,W,3] -> engine frames [n_out, *frame_shape] (datasets/build.py:131-136 semantics);
+        image_view() strips the zero columns."""
         assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
         frames = frames.contiguous()
         n, H, W, _ = frames.shape
@@ -118,7 +124,7 @@ class Engine:
                 raise IndexError("src_index entry beyond the last frame")
         else:
             n_out = n
-        out = torch.empty((n_out, 224, 224, 4), dtype=self.frame_dtype, device=self.device)
+        out = torch.empty((n_out,) + self.frame_shape, dtype=self.frame_dtype, device=self.device)
         check(self.lib.wd_preprocess_u8(self.h, _ptr(frames), n, H, W, _ptr(src_index), n_out, float(in_scale),
                                         _ptr(out), _stream_ptr(self.device)))
         return out
@@ -127,15 +133,19 @@ class Engine:
         """x: cuda fp32 [F,3,224,224] normalised (what the reference module takes) -> engine frames."""
         assert x.is_cuda and x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224)
         x = x.to(torch.float32).contiguous()
-        out = torch.empty((x.shape[0], 224, 224, 4), dtype=self.frame_dtype, device=self.device)
+        out = torch.empty((x.shape[0],) + self.frame_shape, dtype=self.frame_dtype, device=self.device)
         check(self.lib.wd_pack_nchw_f32(self.h, _ptr(x), x.shape[0], _ptr(out), _stream_ptr(self.device)))
         return out
 
+    def image_view(self, frames: torch.Tensor) -> torch.Tensor:
+        """Engine frames -> the [n,224,224,3] image they hold (a view: no zero columns, no padding channel)."""
+        return frames[:, :, self.frame_pad:self.frame_pad + 224, :3]
+
     def forward(self, frames: torch.Tensor, threshold: float = 0.5, softmax: bool = True,
                 timed: bool = False):
-        """frames [n_clips*8,224,224,4] -> (logits [n,C] f32, probs [n,C] f32, state [n] i32[, op_ms])."""
+        """frames [n_clips*8, *frame_shape] -> (logits [n,C] f32, probs [n,C] f32, state [n] i32[, op_ms])."""
         assert frames.is_cuda and frames.dtype == self.frame_dtype and frames.is_contiguous()
-        assert frames.shape[0] % 8 == 0 and tuple(frames.shape[1:]) == (224, 224, 4)
+        assert frames.shape[0] % 8 == 0 and tuple(frames.shape[1:]) == self.frame_shape
         n = frames.shape[0] // 8
         logits = torch.empty((n, self.num_class), dtype=torch.float32, device=self.device)
         probs = torch.empty_like(logits)
