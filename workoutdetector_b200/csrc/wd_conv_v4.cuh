@@ -52,7 +52,8 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     const ConvArgs& a = p.c;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // pointer arithmetic on the shared array (not an integer round trip) keeps the address space visible: LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sB = smem + p.off_b;
     uint8_t* sOut = smem + p.off_out;

@@ -2,7 +2,7 @@
 //
 // Replaces torchvision ResNet.conv1 / bn1 / relu / maxpool as used by the reference (workoutdetector/models/tsm.py:268,
 // torchvision resnet.py `_forward_impl`).  The 112x112x64 stem activation (1.6 MB per frame in bf16) is never
-// written to HBM: a CTA walks down a strip of 15 conv columns, keeps the last four ReLU'd conv rows in shared memory
+// written to HBM: a CTA walks down a strip of 15 conv columns, keeps the vertical 3-max of the ReLU'd conv rows in registers
 // and emits one pooled row (7 pooled columns x 8 segments x 64 channels = 7 KiB, contiguous in the T-inner layout)
 // for every second conv row.  HBM traffic per frame drops from 0.4 (in) + 1.6 (stem out) + 1.6 (pool in) + 0.4 MB
 // to 0.43 + 0.4 MB.
@@ -29,11 +29,11 @@ namespace wd {
 constexpr int kFramePitch = 240;  // pixels per padded frame row (bf16 engine frames)
 constexpr int kFramePad = 8;      // zero columns left of the image
 
-constexpr int kSpPairs = 6;                 // ring of input-row pairs
+constexpr int kSpPairs = 8;                 // ring of input-row pairs (4 live + 4 in flight)
 constexpr int kSpBox = 128 * 64;            // one TMA box: 128 rows x 64 B
 constexpr int kSpPairBytes = 2 * kSpBox;    // 16 KiB
 constexpr int kSpWBytes = 7 * 64 * 64;      // 7 filter rows x [64 co x 64 B]
-constexpr int kSpRowSlots = 4;              // ReLU'd conv rows kept for pooling
+constexpr int kSpRowSlots = 2;              // double-buffered vertical maxima (one 128-row slab per pooled row)
 constexpr int kSpRowBytes = 128 * 128;      // 128 rows x 64 ch bf16
 constexpr int kSpOffW = kSpPairs * kSpPairBytes;
 constexpr int kSpOffRows = kSpOffW + kSpWBytes;
@@ -48,6 +48,12 @@ struct StemPoolArgs {
     int num_units;  // clips * (56 / seg_rows) * 8 strips
 };
 
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
 // K-major SWIZZLE_64B descriptor: 8-row groups are 512 B apart.
 constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint64_t umma_desc64_from_lo(uint32_t lo) {
@@ -58,7 +64,8 @@ __global__ void __launch_bounds__(192, 1)
 stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
                  const StemPoolArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // pointer arithmetic on the shared array (not an integer round trip) keeps the address space visible: LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sW = smem + kSpOffW;
     uint8_t* sRows = smem + kSpOffRows;
@@ -113,10 +120,15 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 
     if (warp < 4) {
         // ==========================================================================================
-        // Epilogue + pooling (128 threads)
+        // Epilogue + pooling (128 threads).  The vertical 3-max runs in registers (a thread owns the same
+        // (column, segment) row of every conv row); only the finished vertical maxima go through shared memory for
+        // the horizontal 3-max, once per pooled row.
         // ==========================================================================================
         const int m = warp * 32 + lane;  // tile row = TMEM lane: ow_local = m >> 3, t = m & 7
         const uint32_t sw = m & 7;
+        uint32_t prev_odd[32], accv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) prev_odd[i] = accv[i] = 0u;
         int tile_iter = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             int clip, ph0, strip;
@@ -124,6 +136,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             const int oh_lo = max(0, 2 * ph0 - 1);
             const int oh_hi = 2 * (ph0 + p.seg_rows) - 1;
             const bool zero_row = (strip == 0 && m < 8);  // conv column -1 is pool padding
+            bool have_prev = false;                       // prev_odd holds conv row oh-1 of this unit
             for (int oh = oh_lo; oh <= oh_hi; ++oh, ++tile_iter) {
                 const int acc = tile_iter & 1;
                 mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
@@ -132,58 +145,60 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr, v0);
                 tmem_ld32(taddr + 32, v1);
+                float4 bb[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) bb[i] = reinterpret_cast<const float4*>(sBias)[i];
                 tmem_ld_wait();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
                 __syncwarp();
-                uint8_t* rowbuf = sRows + (oh & (kSpRowSlots - 1)) * kSpRowBytes + m * 128;
+                uint32_t cur[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t* v = (i < 8) ? (v0 + i * 4) : (v1 + (i - 8) * 4);
+                    cur[2 * i] = pack_bf16x2_relu(__uint_as_float(v[0]) + bb[i].x, __uint_as_float(v[1]) + bb[i].y);
+                    cur[2 * i + 1] = pack_bf16x2_relu(__uint_as_float(v[2]) + bb[i].z, __uint_as_float(v[3]) + bb[i].w);
+                }
+                if (!(oh & 1)) {  // even row 2ph: rows 2ph-1 (if any) and 2ph
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) accv[i] = have_prev ? bf16x2_max(prev_odd[i], cur[i]) : cur[i];
+                    continue;
+                }
+                const bool emit = oh != 2 * ph0 - 1;  // the unit's leading odd row belongs to the previous band
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    accv[i] = bf16x2_max(accv[i], cur[i]);
+                    prev_odd[i] = cur[i];
+                }
+                have_prev = true;
+                if (!emit) continue;
+                const int ph = (oh - 1) >> 1;
+                uint8_t* hb = sRows + (ph & 1) * kSpRowBytes;
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
-                    const uint32_t* v = (c8 < 4) ? (v0 + c8 * 8) : (v1 + (c8 - 4) * 8);
-                    const float4 b0 = *reinterpret_cast<const float4*>(sBias + c8 * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sBias + c8 * 8 + 4);
-                    uint4 o;
-                    o.x = pack_bf16x2_relu(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y);
-                    o.y = pack_bf16x2_relu(__uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);
-                    o.z = pack_bf16x2_relu(__uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y);
-                    o.w = pack_bf16x2_relu(__uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w);
+                    uint4 o = make_uint4(accv[4 * c8], accv[4 * c8 + 1], accv[4 * c8 + 2], accv[4 * c8 + 3]);
                     if (zero_row) o = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(rowbuf + ((c8 ^ sw) << 4)) = o;
+                    *reinterpret_cast<uint4*>(hb + m * 128 + ((c8 ^ sw) << 4)) = o;
                 }
-                // all four warps have written conv row oh (and finished pooling the previous rows)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int ph = (oh - 1) >> 1;
-                if ((oh & 1) && ph >= ph0) {
-                    // pooled row ph = max over conv rows 2ph-1 .. 2ph+1 (= oh-2 .. oh) and local columns 2j .. 2j+2
-                    const int r_first = (oh - 2 < 0) ? oh - 1 : oh - 2;
-                    __nv_bfloat16* orow =
-                        p.out + ((((size_t)clip * 56 + ph) * 56 + strip * 7) * 8) * 64;  // 7*8*64 contiguous elements
-                    for (int idx = tid; idx < 7 * 64; idx += 128) {
-                        const int j = idx >> 6;
-                        const int t = (idx >> 3) & 7;
-                        const int cv = idx & 7;
-                        __nv_bfloat162 best[4];
-                        bool first = true;
-                        for (int r = r_first; r <= oh; ++r) {
-                            const uint8_t* rb = sRows + (r & (kSpRowSlots - 1)) * kSpRowBytes;
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // vertical maxima of all 16 columns are in hb
+                __nv_bfloat16* orow = p.out + ((((size_t)clip * 56 + ph) * 56 + strip * 7) * 8) * 64;  // 7*8*64 contiguous
+                for (int idx = tid; idx < 7 * 64; idx += 128) {
+                    const int j = idx >> 6;
+                    const int t = (idx >> 3) & 7;
+                    const int cv = idx & 7;
+                    uint4 q[3];
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                const int mm = (2 * j + dx) * 8 + t;
-                                const uint4 q = *reinterpret_cast<const uint4*>(rb + mm * 128 + ((cv ^ (mm & 7)) << 4));
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-                                if (first) {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) best[e] = h[e];
-                                    first = false;
-                                } else {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) best[e] = __hmax2(best[e], h[e]);
-                                }
-                            }
-                        }
-                        *reinterpret_cast<uint4*>(orow + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(best);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int mm = (2 * j + dx) * 8 + t;
+                        q[dx] = *reinterpret_cast<const uint4*>(hb + mm * 128 + ((cv ^ (mm & 7)) << 4));
                     }
+                    uint4 r;
+                    r.x = bf16x2_max(bf16x2_max(q[0].x, q[1].x), q[2].x);
+                    r.y = bf16x2_max(bf16x2_max(q[0].y, q[1].y), q[2].y);
+                    r.z = bf16x2_max(bf16x2_max(q[0].z, q[1].z), q[2].z);
+                    r.w = bf16x2_max(bf16x2_max(q[0].w, q[1].w), q[2].w);
+                    *reinterpret_cast<uint4*>(orow + (size_t)idx * 8) = r;
                 }
             }
         }
