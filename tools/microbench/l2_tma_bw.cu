@@ -67,23 +67,24 @@ int main() {
     cudaDriverEntryPointQueryResult qres;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     EncodeFn encode = (EncodeFn)fn;
-    const size_t rows_total = 148 * 1024;  // 148 * 1024 * 128 B = 19.4 MB: L2 resident
+    const size_t rows_total = 148 * 1024;  // 148 * 1024 rows; at stride 128 B = 19.4 MB: L2 resident
     void* buf;
-    cudaMalloc(&buf, rows_total * 128);
-    cudaMemset(buf, 1, rows_total * 128);
+    cudaMalloc(&buf, rows_total * 512);
+    cudaMemset(buf, 1, rows_total * 512);
     cudaFuncSetAttribute(tma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    for (int bulk = 0; bulk < 2; ++bulk)
-    for (int nwarps : {1, 2, 4})
+    for (int stride : {128, 256, 512})
+    for (int bulk = 0; bulk < 1; ++bulk)
+    for (int nwarps : {2, 4})
     for (int mode = 0; mode < 1; ++mode)
         for (int rows : {64, 128, 256})
-            for (int stages : {1, 2, 4}) {
+            for (int stages : {2, 4}) {
                 if ((size_t)nwarps * stages * rows * 128 > 200 * 1024) continue;
                 CUtensorMap map;
                 cuuint64_t dims[2] = {64, rows_total};
-                cuuint64_t strides[1] = {128};
+                cuuint64_t strides[1] = {(cuuint64_t)stride};
                 cuuint32_t box[2] = {64, (cuuint32_t)rows};
                 cuuint32_t es[2] = {1, 1};
                 if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -102,7 +103,7 @@ int main() {
                 float ms;
                 cudaEventElapsedTime(&ms, e0, e1);
                 const double bytes = 148.0 * (iters / nwarps * nwarps) * rows * 128;
-                printf("bulk %d warps %d mode %d box %3d rows (%5d B) stages %2d: %7.3f ms  %6.2f TB/s  (%5.1f B/clk/SM @1.965GHz) %s\n", bulk, nwarps, mode, rows,
+                printf("stride %d bulk %d warps %d mode %d box %3d rows (%5d B) stages %2d: %7.3f ms  %6.2f TB/s  (%5.1f B/clk/SM @1.965GHz) %s\n", stride, bulk, nwarps, mode, rows,
                        rows * 128, stages, ms, bytes / ms / 1e9, bytes / ms / 1e6 / 148 / 1.965,
                        err == cudaSuccess ? "" : cudaGetErrorString(err));
             }

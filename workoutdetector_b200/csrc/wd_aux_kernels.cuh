@@ -7,6 +7,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "wd_ptx.cuh"
+
 namespace wd {
 
 // ------------------------------------------------------------------------------------------------
@@ -243,6 +245,8 @@ head_kernel(const T* __restrict__ feat,  // [clips, rows_per_clip, C]
             float* __restrict__ probs,   // nullable
             int32_t* __restrict__ state  // nullable
 ) {
+    pdl_grid_dependency_wait();  // features come from the last convolution (PDL launch)
+    pdl_launch_dependents();
     extern __shared__ float sm[];  // C feature means, classes logits, then 4 x C partial sums
     float* sfeat = sm;
     float* slog = sm + C;

@@ -40,8 +40,17 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
     return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
 }
 
+// Debug timeline: role r of CTA 0 appends clock() samples to trace[r*2048 ...] (tools/trace_conv.py reads them).
+struct Tracer {
+    uint32_t* p;
+    int n;
+    __device__ __forceinline__ void mark() {
+        if (p && n < 2040) p[n++] = (uint32_t)clock();
+    }
+};
+
 template <int BN, int AMODE, bool HAS_RES>
-__global__ void __launch_bounds__((AMODE == A_TMA || AMODE == A_STRIP) ? 224 : 320, 1)
+__global__ void __launch_bounds__(AMODE == A_TMA ? 224 : (AMODE == A_STRIP ? 288 : 320), 1)
 conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap rmap,
                const __grid_constant__ CUtensorMap omap16, const ConvArgs3 p) {
@@ -61,8 +70,11 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
     uint64_t* a_full = bars;                  // [8]
     uint64_t* a_empty = bars + 8;             // [8]
-    uint64_t* b_full = bars + 16;             // [8]
-    uint64_t* b_empty = bars + 24;            // [8]
+    // A_TMA with streamed W: A and W of a k-block share ONE full / empty barrier pair, so the MMA issuer pays one
+    // mbarrier round trip per k-block (tools/trace_conv.py: each try_wait costs it 270-560 cycles even when complete)
+    const bool merged = (AMODE == A_TMA) && !p.w_resident && p.a_stages == p.b_stages;
+    uint64_t* b_full = merged ? bars : bars + 16;        // [8]
+    uint64_t* b_empty = merged ? bars + 8 : bars + 24;   // [8]
     uint64_t* tmem_full_bar = bars + 32;      // [2]
     uint64_t* tmem_empty_bar = bars + 34;     // [2]
     uint64_t* w_bar = bars + 36;              // [1]
@@ -70,6 +82,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 56);
     float* sBias = reinterpret_cast<float*>(bars + 64);  // BN floats (the plan reserves 2 KiB for barriers + bias)
 
+    pdl_launch_dependents();  // the next layer may start its prologue / weight loads on SMs this grid has left
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
     const int lane = tid & 31;
@@ -85,10 +98,10 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             if (HAS_RES) tma_prefetch_desc(&rmap);
             if (kStrip) tma_prefetch_desc(&omap16);
             for (int s = 0; s < 8; ++s) {
-                mbar_init(&a_full[s], kTmaA ? 1 : 128);
+                mbar_init(&bars[s], merged ? 2 : (kStrip ? 3 : (kTmaA ? 1 : 128)));
                 mbar_init(&a_empty[s], 1);
-                mbar_init(&b_full[s], 1);
-                mbar_init(&b_empty[s], 1);
+                mbar_init(&bars[16 + s], 1);
+                mbar_init(&bars[24 + s], 1);
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
@@ -111,6 +124,9 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
+    // Everything above (and the weight loads of warp 4) overlaps the previous layer; activations may only be touched
+    // after it has completed.  The MMA issuer never touches global memory.
+    if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
 
     // tile -> first output row of the tile
     auto tile_m0 = [&](int m_tile) -> int {
@@ -138,6 +154,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         uint32_t chunk_idx = 0;  // running chunk counter across tiles
         int tile_iter = 0;
         const bool relu = a.relu != 0;
+        Tracer etr{(p.trace && blockIdx.x == 0) ? p.trace + 3 * 2048 : nullptr, 0};
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const int mrow = tile_m0(tile / a.n_tiles) + warp * 32;
             const int acc = tile_iter & 1;
@@ -161,9 +178,12 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                     }
                 }
                 if (c == 0) {
+                    if (warp == 0) etr.mark();
                     mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+                    if (warp == 0) etr.mark();
                     tc_fence_after_sync();
                 }
+                if (warp == 0) etr.mark();  // e0: chunk start (after residual issue / tmem_full wait)
                 // ---- all loads of this chunk first: residual slab, bias, accumulator ----
                 uint4 rr[8];
                 const uint32_t rslot = chunk_idx % kResDepth;
@@ -177,10 +197,12 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 const float4* bsrc = reinterpret_cast<const float4*>(sBias + c * 64);
 #pragma unroll
                 for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
+                if (warp == 0) etr.mark();  // e1: residual landed, LDS issued
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr + c * 64, v0);
                 tmem_ld32(taddr + c * 64 + 32, v1);
                 tmem_ld_wait();
+                if (warp == 0) etr.mark();  // e2: accumulator in registers
                 if (c == kChunks - 1) {  // accumulator drained: hand it back to the MMA issuer
                     tc_fence_before_sync();
                     __syncwarp();
@@ -189,6 +211,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 }
                 if (elect_one()) tma_store_wait_read1();  // the store that last read this out slot is done reading
                 __syncwarp();
+                if (warp == 0) etr.mark();  // e3: out slab free
                 uint8_t* obuf = my_out + (chunk_idx & 1) * kEpiSlab + row_off;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -216,8 +239,10 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                     }
                     *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+                if (warp == 0) etr.mark();  // e4: math + STS done
                 fence_proxy_async_smem();
                 __syncwarp();
+                if (warp == 0) etr.mark();  // e5: proxy fence done
                 if (elect_one()) {
                     // strip tiles have 112 rows: the last warp stores a 16-row box so it never touches the next strip
                     if (kStrip && warp == 3)
@@ -244,11 +269,14 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             __syncwarp();
         } else {
             uint32_t it = 0;
+            Tracer tr{(p.trace && blockIdx.x == 0) ? p.trace + 1 * 2048 : nullptr, 0};
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int as = 0; as < a_steps; ++as) {
                     for (int tap = 0; tap < kTaps; ++tap, ++it) {
                         const int slot = it % p.b_stages;
+                        tr.mark();
                         mbar_wait(&b_empty[slot], ((it / p.b_stages) & 1) ^ 1);
+                        tr.mark();
                         const int kbi = kStrip ? tap * a.cin_blocks + as : as;
                         if (elect_one()) {
                             mbar_arrive_expect_tx(&b_full[slot], kBTile);
@@ -268,15 +296,19 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         const uint32_t sB_lo = umma_desc_lo(smem_u32(sB));
         uint32_t ita = 0, itb = 0;
         int tile_iter = 0;
+        Tracer tr{(p.trace && blockIdx.x == 0) ? p.trace : nullptr, 0};
         if (p.w_resident) mbar_wait(w_bar, 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const int acc = tile_iter & 1;
+            tr.mark();
             mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int as = 0; as < a_steps; ++as, ++ita) {
                 const int aslot = ita % p.a_stages;
+                tr.mark();
                 mbar_wait(&a_full[aslot], (ita / p.a_stages) & 1);
+                tr.mark();
                 if (!kTmaA) fence_proxy_async_smem();
                 tc_fence_after_sync();
                 const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * p.a_stage_bytes) >> 4);
@@ -287,9 +319,13 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                     const int kbi = kStrip ? tap * a.cin_blocks + as : as;
                     if (p.w_resident) {
                         b_lo = sB_lo + ((uint32_t)(kbi * kBTile) >> 4);
+                    } else if (merged) {
+                        bslot = aslot;
+                        b_lo = sB_lo + ((uint32_t)(bslot * kBTile) >> 4);
                     } else {
                         bslot = itb % p.b_stages;
                         mbar_wait(&b_full[bslot], (itb / p.b_stages) & 1);
+                        tr.mark();
                         tc_fence_after_sync();
                         b_lo = sB_lo + ((uint32_t)(bslot * kBTile) >> 4);
                         ++itb;
@@ -304,7 +340,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                         umma_bf16_ss(d_tmem, adesc, bdesc, idesc, first);
 #pragma unroll
                         for (int k = 1; k < kTileK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
-                        if (!p.w_resident) umma_commit(&b_empty[bslot]);
+                        if (!p.w_resident && !merged) umma_commit(&b_empty[bslot]);
                         if (tap == kTaps - 1) {
                             umma_commit(&a_empty[aslot]);
                             if (as == a_steps - 1) umma_commit(&tmem_full_bar[acc]);
@@ -318,34 +354,57 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         // ==========================================================================================
         // A producer by TMA (warp 6)
         // ==========================================================================================
-        if (warp == 6) {
+        // strip: warps 6, 7, 8 each own one input row (r = warp - 6) of every stage; a single issuing thread tops out
+        // near one 16 KiB box per ~700 cycles (tools/microbench/tma_shapes.cu), three rows in parallel do not
+        if (warp == 6 || kStrip) {
+            const int prow = warp - 6;  // strip: input row h-1+prow
+            // Tile coordinates advance incrementally (no integer division on the producer's critical path: its loop
+            // latency is part of the ring round trip that bounds the k-block rate, tools/trace_conv.py).
+            // m_tile(i) = blockIdx.x / n_tiles + i * m_step; strip tiles decompose into (ws, h, n).
+            const int m_step = (int)gridDim.x / a.n_tiles;
+            int m_tile = (int)blockIdx.x / a.n_tiles;
+            int ws = 0, h = 0, n = 0, step_ws = 0, step_h = 0, step_n = 0;
+            if (kStrip) {
+                ws = m_tile % p.tiles_w;
+                const int q = m_tile / p.tiles_w;
+                h = q % a.Hout;
+                n = q / a.Hout;
+                step_ws = m_step % p.tiles_w;
+                const int sq = m_step / p.tiles_w;
+                step_h = sq % a.Hout;
+                step_n = sq / a.Hout;
+            }
             uint32_t it = 0;
+            Tracer tr{(p.trace && blockIdx.x == 0 && warp == 6) ? p.trace + 2 * 2048 : nullptr, 0};
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / a.n_tiles;
+                const int px0 = (m_tile * kTileM) >> 3;
                 for (int as = 0; as < a_steps; ++as, ++it) {
                     const int slot = it % p.a_stages;
+                    tr.mark();
                     mbar_wait(&a_empty[slot], ((it / p.a_stages) & 1) ^ 1);
+                    tr.mark();
                     uint8_t* dst = sA + slot * p.a_stage_bytes;
+                    const int c = as * kTileK;
                     if (elect_one()) {
-                        if (kStrip) {
-                            const int ws = m_tile % p.tiles_w;
-                            const int q = m_tile / p.tiles_w;
-                            const int h = q % a.Hout;
-                            const int n = q / a.Hout;
-                            mbar_arrive_expect_tx(&a_full[slot], 3 * 16384);
-#pragma unroll
-                            for (int r = 0; r < 3; ++r)  // rows h-1, h, h+1; pixels w0-1 .. w0+14; OOB -> zeros (padding)
-                                tma_load_5d(&amap, &a_full[slot], dst + r * 16384, as * kTileK, 0,
-                                            ws * kStripPixels - 1, h - 1 + r, n);
+                        if (kStrip) {  // rows h-1, h, h+1; pixels w0-1 .. w0+14; OOB -> zeros (padding)
+                            mbar_arrive_expect_tx(&a_full[slot], 16384);
+                            tma_load_5d(&amap, &a_full[slot], dst + prow * 16384, c, 0, ws * kStripPixels - 1, h - 1 + prow, n);
                         } else {
-                            const int c = as * kTileK;
                             int dt = 0;
                             if (a.fold) dt = (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
                             mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
-                            tma_load_3d(&amap, &a_full[slot], dst, c, dt, (m_tile * kTileM) >> 3);
+                            tma_load_3d(&amap, &a_full[slot], dst, c, dt, px0);
                         }
                     }
                     __syncwarp();
+                }
+                m_tile += m_step;
+                if (kStrip) {
+                    ws += step_ws;
+                    if (ws >= p.tiles_w) { ws -= p.tiles_w; ++h; }
+                    h += step_h;
+                    while (h >= a.Hout) { h -= a.Hout; ++n; }
+                    n += step_n;
                 }
             }
         }

@@ -295,6 +295,25 @@ int build_plan(wd_engine* e) {
 // ---------------------------------------------------------------------------------------------------
 // Launch helpers
 // ---------------------------------------------------------------------------------------------------
+int g_pdl = getenv("WD_PDL") ? atoi(getenv("WD_PDL")) : 1;  // programmatic dependent launch between layers (option "pdl")
+
+// Launch with programmatic stream serialization: the kernel may begin (prologue, weight loads) while its predecessor
+// in the stream is still running; it calls griddepcontrol.wait before touching activations (wd_ptx.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                       Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 template <int BN, int STAGES, int AMODE>
 int launch_conv_t(const CUtensorMap& wmap, const CUtensorMap& amap, const wd::ConvArgs& a, cudaStream_t st) {
     using L = wd::ConvSmem<BN, STAGES>;
@@ -440,6 +459,12 @@ int launch_v3(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
 }
 
 
+uint32_t* g_trace = nullptr;  // debug timeline buffer (WD_TRACE=<file> with the single-layer hooks)
+
+// L2 prefetch distance of the A operand in k-blocks (option "prefetch_kblocks"; WD_PREFETCH_KBLOCKS for the
+// engine-less single-layer hooks)
+int g_prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETCH_KBLOCKS")) : 0;
+
 template <int BN, int AMODE, bool RES>
 int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
@@ -463,9 +488,10 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.off_res = sp.off_res;
     p.off_bar = sp.off_bar;
     p.tiles_w = AMODE == wd::A_STRIP ? a.Wout / wd::kStripPixels : 1;
-    const unsigned threads = (AMODE == wd::A_TMA || AMODE == wd::A_STRIP) ? 224 : 320;
-    kfn<<<(unsigned)grid, threads, sp.total, st>>>(c.wmap, c.amap, c.omap, c.rmap, c.omap16, p);
-    WD_CUDA(cudaGetLastError());
+    p.prefetch_kblocks = g_prefetch_kblocks;
+    p.trace = g_trace;
+    const unsigned threads = AMODE == wd::A_TMA ? 224 : (AMODE == wd::A_STRIP ? 288 : 320);
+    WD_CUDA(launch_pdl(kfn, (unsigned)grid, threads, (size_t)sp.total, st, c.wmap, c.amap, c.omap, c.rmap, c.omap16, p));
     return WD_OK;
 }
 
@@ -677,8 +703,7 @@ int launch_stem_pool(wd_engine* e, const ConvLayer& c, const void* frames, void*
     p.seg_rows = e->stem_seg_rows;
     p.num_units = n_clips * (56 / p.seg_rows) * 8;
     const int grid = std::min(p.num_units, e->sm_count);
-    wd::stem_pool_kernel<<<grid, 192, wd::kSpSmem, st>>>(amap, c.wmap, p);
-    WD_CUDA(cudaGetLastError());
+    WD_CUDA(launch_pdl(wd::stem_pool_kernel, (unsigned)grid, 192u, (size_t)wd::kSpSmem, st, amap, c.wmap, p));
     return WD_OK;
 }
 
@@ -749,9 +774,9 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                     static_cast<const float*>(in), e->fc_w, e->fc_b, rows, C, e->desc.num_class, threshold,
                     apply_softmax, logits, probs, state);
             else
-                wd::head_kernel<__nv_bfloat16><<<n_clips, wd::kHeadThreads, smem, st>>>(
-                    static_cast<const __nv_bfloat16*>(in), e->fc_w, e->fc_b, rows, C, e->desc.num_class, threshold,
-                    apply_softmax, logits, probs, state);
+                WD_CUDA(launch_pdl(wd::head_kernel<__nv_bfloat16>, (unsigned)n_clips, (unsigned)wd::kHeadThreads, smem, st,
+                                   static_cast<const __nv_bfloat16*>(in), (const float*)e->fc_w, (const float*)e->fc_b, rows,
+                                   C, (int)e->desc.num_class, threshold, apply_softmax, logits, probs, state));
             WD_CUDA(cudaGetLastError());
             ++e->launches;
         }
@@ -908,6 +933,11 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     } else if (!strcmp(key, "persistent")) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
+    } else if (!strcmp(key, "pdl")) {
+        g_pdl = value ? 1 : 0;
+    } else if (!strcmp(key, "prefetch_kblocks")) {
+        if (value < 0 || value > 256) return fail(WD_ERR_INVALID, "prefetch_kblocks must be in [0, 256]");
+        g_prefetch_kblocks = value;
     } else if (!strcmp(key, "stem_seg_rows")) {
         if (value < 1 || 56 % value != 0) return fail(WD_ERR_INVALID, "stem_seg_rows must divide 56");
         e->stem_seg_rows = value;
@@ -1207,7 +1237,23 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
             wd::ConvArgs a = conv_args(c, x, y, residual, clips);
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+            const char* trace_path = getenv("WD_TRACE");
+            if (trace_path) {
+                cudaMalloc(&g_trace, 4 * 2048 * sizeof(uint32_t));
+                cudaMemset(g_trace, 0, 4 * 2048 * sizeof(uint32_t));
+            }
             rc = launch_any(c, a, persistent, sms, nullptr);
+            if (trace_path) {
+                cudaDeviceSynchronize();
+                std::vector<uint32_t> h(4 * 2048);
+                cudaMemcpy(h.data(), g_trace, h.size() * 4, cudaMemcpyDeviceToHost);
+                cudaFree(g_trace);
+                g_trace = nullptr;
+                if (FILE* f = fopen(trace_path, "wb")) {
+                    fwrite(h.data(), 4, h.size(), f);
+                    fclose(f);
+                }
+            }
             if (rc == WD_OK && iters > 0 && ms_out) {
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0);

@@ -31,6 +31,16 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  launch_dependents: the next kernel of the stream may start its prologue
+// (barrier init, TMEM allocation, weight loads) while this grid is still running.  grid_dependency_wait: blocks until
+// the previous grid has completed and its memory is visible — required before the first access to any activation
+// buffer (read OR write: the workspace buffers rotate, so our output may be the previous kernel's input).
+// Both are no-ops when the kernel was not launched with the programmatic-serialization attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -141,6 +151,27 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* ba
         : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
           "r"(c3), "r"(c4)
         : "memory");
+}
+
+// L2 prefetch of a tensor box: no shared memory, no completion tracking.  Used to pull the A operand of tiles that
+// are still several microseconds away out of HBM, so that the real load later pays L2 latency only.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {

@@ -78,6 +78,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
     float* sBias = reinterpret_cast<float*>(bars + 24);  // 64 floats
 
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
@@ -124,6 +125,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         // (column, segment) row of every conv row); only the finished vertical maxima go through shared memory for
         // the horizontal 3-max, once per pooled row.
         // ==========================================================================================
+        pdl_grid_dependency_wait();  // the output buffer may still be read by the previous forward's kernels
         const int m = warp * 32 + lane;  // tile row = TMEM lane: ow_local = m >> 3, t = m & 7
         const uint32_t sw = m & 7;
         uint32_t prev_odd[32], accv[32];
@@ -211,6 +213,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             for (int r = 0; r < 7; ++r) tma_load_2d(&wmap, w_bar, sW + r * 4096, r * 32, 0);
         }
         __syncwarp();
+        pdl_grid_dependency_wait();  // frames are written by the preprocess kernel
         uint32_t it = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             int clip, ph0, strip;
