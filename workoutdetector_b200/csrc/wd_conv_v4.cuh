@@ -49,8 +49,17 @@ struct Tracer {
     }
 };
 
-template <int BN, int AMODE, bool HAS_RES>
-__global__ void __launch_bounds__(AMODE == A_TMA ? 224 : (AMODE == A_STRIP ? 288 : 320), 1)
+// Residual 1x1 layers (conv3 of every bottleneck) are epilogue-bound once K is small (tools/trace_conv.py: ~1450
+// cycles per 64-column chunk, 40 % of it dependent-issue latency of one warp per scheduler, the rest issue latency
+// of TMA / mbarrier instructions).  They run EIGHT epilogue warps (two per scheduler, each pair splits the columns
+// of a TMEM lane quarter) and add the residual IN PLACE in the slab the TMA load delivered it to, which is then the
+// source of the TMA store: three 4 KiB slabs per warp, two residual chunks in flight per warp (64 KiB per SM).
+// Chosen per layer by the host (K >= 256: layers 3-4; the HBM-bound conv3 of layers 1-2 is faster with four warps).
+template <int AMODE, bool EPI8>
+constexpr int kThreadsFor = EPI8 ? 384 : (AMODE == A_TMA ? 224 : (AMODE == A_STRIP ? 288 : 320));
+
+template <int BN, int AMODE, bool HAS_RES, bool EPI8 = false>
+__global__ void __launch_bounds__(kThreadsFor<AMODE, EPI8>, 1)
 conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap rmap,
                const __grid_constant__ CUtensorMap omap16, const ConvArgs3 p) {
@@ -58,6 +67,9 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     constexpr bool kStrip = (AMODE == A_STRIP);
     constexpr bool kTmaA = (AMODE == A_TMA || AMODE == A_STRIP);
     constexpr int kTaps = kStrip ? 9 : 1;  // W steps per A stage
+    constexpr bool kEpi8 = EPI8;
+    static_assert(!EPI8 || (AMODE == A_TMA && HAS_RES && BN >= 128), "8-warp epilogue: residual 1x1 TMA layers only");
+    constexpr int kSlabs = 3;              // kEpi8: in-place residual/output slabs per epilogue warp
     const ConvArgs& a = p.c;
 
     extern __shared__ uint8_t smem_raw[];
@@ -105,10 +117,12 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], 4);
+                mbar_init(&tmem_empty_bar[s], kEpi8 ? 8 : 4);
             }
             mbar_init(w_bar, 1);
             for (int s = 0; s < 4 * kResDepth; ++s) mbar_init(&res_bar[s], 1);
+            if (kEpi8)
+                for (int s = 0; s < 8 * kSlabs; ++s) mbar_init(&bars[192 + s], 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -138,7 +152,106 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         return m_tile * kTileM;
     };
 
-    if (warp < 4) {
+    if (kEpi8 && (warp < 4 || warp >= 8)) {
+        // ==========================================================================================
+        // Eight epilogue warps, residual added in place (see kEpi8For)
+        // ==========================================================================================
+        const int egrp = warp >> 3;            // column half of the tile
+        const int quarter = warp & 3;          // TMEM lane quarter
+        const int eidx = egrp * 4 + quarter;
+        uint8_t* my_slabs = sOut + eidx * kSlabs * kEpiSlab;   // sOut .. sOut + 96 KiB (out + res regions of the plan)
+        uint64_t* my_bar = bars + 192 + eidx * kSlabs;
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        constexpr int kCpt = BN >= 128 ? BN / 128 : 1;  // chunks per tile per warp
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const uint32_t total = (uint32_t)my_tiles * kCpt;
+        const bool relu = a.relu != 0;
+        auto issue_res = [&](uint32_t q) {     // residual chunk q of this warp -> slab q % kSlabs
+            const int t2 = (int)blockIdx.x + (int)(q / kCpt) * (int)gridDim.x;
+            const int rn0 = cta_n0 + (egrp * kCpt + (int)(q % kCpt)) * 64;
+            const int rm = tile_m0(t2 / a.n_tiles) + quarter * 32;
+            const uint32_t slot = q % kSlabs;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&my_bar[slot], kEpiSlab);
+                tma_load_2d(&rmap, &my_bar[slot], my_slabs + slot * kEpiSlab, rn0, rm);
+            }
+            __syncwarp();
+        };
+        if (total > 0) issue_res(0);
+        if (total > 1) issue_res(1);
+        uint32_t j = 0;
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int mrow = tile_m0(tile / a.n_tiles) + quarter * 32;
+            const int acc = tile_iter & 1;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + egrp * (BN / 2);
+#pragma unroll 1
+            for (int cc = 0; cc < kCpt; ++cc, ++j) {
+                const uint32_t slot = j % kSlabs;
+                uint8_t* slab = my_slabs + slot * kEpiSlab + row_off;
+                if (cc == 0) {
+                    mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+                    tc_fence_after_sync();
+                }
+                mbar_wait(&my_bar[slot], (j / kSlabs) & 1);   // residual chunk j has landed in its slab
+                const float* bsrc = sBias + (egrp * kCpt + cc) * 64;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {  // two 32-column halves keep the live registers under the 384-thread cap
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 64 + hf * 32, v);
+                    uint4 rr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) rr[u] = *reinterpret_cast<const uint4*>(slab + (((hf * 4 + u) ^ sw) << 4));
+                    float4 bb[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) bb[u] = reinterpret_cast<const float4*>(bsrc + hf * 32)[u];
+                    tmem_ld_wait();
+                    if (hf == 1 && cc == kCpt - 1) {  // this warp's share of the accumulator is in registers
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                        const uint32_t rw[4] = {rr[u].x, rr[u].y, rr[u].z, rr[u].w};
+                        float f[8] = {__uint_as_float(v[u * 8 + 0]) + b0.x, __uint_as_float(v[u * 8 + 1]) + b0.y,
+                                      __uint_as_float(v[u * 8 + 2]) + b0.z, __uint_as_float(v[u * 8 + 3]) + b0.w,
+                                      __uint_as_float(v[u * 8 + 4]) + b1.x, __uint_as_float(v[u * 8 + 5]) + b1.y,
+                                      __uint_as_float(v[u * 8 + 6]) + b1.z, __uint_as_float(v[u * 8 + 7]) + b1.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            f[2 * q] += __uint_as_float(rw[q] << 16);
+                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                        }
+                        uint32_t o[4];
+                        if (relu) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2_relu(f[2 * q], f[2 * q + 1]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(slab + (((hf * 4 + u) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&omap, my_slabs + slot * kEpiSlab, cta_n0 + (egrp * kCpt + cc) * 64, mrow);
+                    tma_store_commit();
+                    // slab (j+2) % 3 == (j-1) % 3 is free once the store of chunk j-1 has read it (chunk j's may be pending)
+                    if (j + 2 < total) tma_store_wait_read1();
+                }
+                __syncwarp();
+                if (j + 2 < total) issue_res(j + 2);
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp < 4) {
         // ==========================================================================================
         // Epilogue warps: TMEM -> (+bias, +residual, ReLU) -> bf16 -> swizzled smem slab -> TMA store
         // ==========================================================================================
@@ -374,6 +487,8 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 step_h = sq % a.Hout;
                 step_n = sq / a.Hout;
             }
+            const int ahead = (!kStrip && p.prefetch_kblocks > 0) ? (p.prefetch_kblocks + a_steps - 1) / a_steps : 0;
+            const int m_tiles_total = num_tiles / a.n_tiles;
             uint32_t it = 0;
             Tracer tr{(p.trace && blockIdx.x == 0 && warp == 6) ? p.trace + 2 * 2048 : nullptr, 0};
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -394,6 +509,10 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                             if (a.fold) dt = (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
                             mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
                             tma_load_3d(&amap, &a_full[slot], dst, c, dt, px0);
+                            // shallow ring (residual layers keep 96 KiB of slabs): pull the same k-block of the tile
+                            // `ahead` iterations away from HBM into L2 now, so that its load pays L2 latency only
+                            if (ahead > 0 && m_tile + ahead * m_step < m_tiles_total)
+                                tma_prefetch_l2_3d(&amap, c, dt, ((m_tile + ahead * m_step) * kTileM) >> 3);
                         }
                     }
                     __syncwarp();

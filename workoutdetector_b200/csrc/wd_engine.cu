@@ -463,12 +463,14 @@ uint32_t* g_trace = nullptr;  // debug timeline buffer (WD_TRACE=<file> with the
 
 // L2 prefetch distance of the A operand in k-blocks (option "prefetch_kblocks"; WD_PREFETCH_KBLOCKS for the
 // engine-less single-layer hooks)
-int g_prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETCH_KBLOCKS")) : 0;
+int g_prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETCH_KBLOCKS")) : -1;  // -1 = per-layer rule
 
-template <int BN, int AMODE, bool RES>
+int g_epi8 = getenv("WD_EPI8") ? atoi(getenv("WD_EPI8")) : 1;  // 8-warp in-place epilogue for residual layers with K >= 256
+
+template <int BN, int AMODE, bool RES, bool EPI8 = false>
 int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = wd::conv_v4_kernel<BN, AMODE, RES>;
+    auto kfn = wd::conv_v4_kernel<BN, AMODE, RES, EPI8>;
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
@@ -488,9 +490,10 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.off_res = sp.off_res;
     p.off_bar = sp.off_bar;
     p.tiles_w = AMODE == wd::A_STRIP ? a.Wout / wd::kStripPixels : 1;
-    p.prefetch_kblocks = g_prefetch_kblocks;
+    // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
+    p.prefetch_kblocks = (g_prefetch_kblocks >= 0) ? g_prefetch_kblocks : ((sp.a_stages <= 3 && a.kblocks >= 4) ? 4 : 0);
     p.trace = g_trace;
-    const unsigned threads = AMODE == wd::A_TMA ? 224 : (AMODE == wd::A_STRIP ? 288 : 320);
+    const unsigned threads = wd::kThreadsFor<AMODE, EPI8>;
     WD_CUDA(launch_pdl(kfn, (unsigned)grid, threads, (size_t)sp.total, st, c.wmap, c.amap, c.omap, c.rmap, c.omap16, p));
     return WD_OK;
 }
@@ -503,8 +506,13 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
             if (BN == 64 && !res) return launch_v4_t<64, wd::A_STEM, false>(c, a, sm_count, st);
             break;
         case wd::A_TMA:
-            return res ? launch_v4_t<BN, wd::A_TMA, true>(c, a, sm_count, st)
-                       : launch_v4_t<BN, wd::A_TMA, false>(c, a, sm_count, st);
+            if (res) {
+                // epilogue-bound once the K loop is short relative to the 128 x BN output tile: 8 epilogue warps
+                if constexpr (BN >= 128)
+                    if (a.kblocks >= 4 && g_epi8) return launch_v4_t<BN, wd::A_TMA, true, true>(c, a, sm_count, st);
+                return launch_v4_t<BN, wd::A_TMA, true>(c, a, sm_count, st);
+            }
+            return launch_v4_t<BN, wd::A_TMA, false>(c, a, sm_count, st);
         case wd::A_STRIP:
             if (!res) return launch_v4_t<BN, wd::A_STRIP, false>(c, a, sm_count, st);
             break;
@@ -936,7 +944,7 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     } else if (!strcmp(key, "pdl")) {
         g_pdl = value ? 1 : 0;
     } else if (!strcmp(key, "prefetch_kblocks")) {
-        if (value < 0 || value > 256) return fail(WD_ERR_INVALID, "prefetch_kblocks must be in [0, 256]");
+        if (value < -1 || value > 256) return fail(WD_ERR_INVALID, "prefetch_kblocks must be in [-1, 256]");
         g_prefetch_kblocks = value;
     } else if (!strcmp(key, "stem_seg_rows")) {
         if (value < 1 || 56 % value != 0) return fail(WD_ERR_INVALID, "stem_seg_rows must divide 56");
