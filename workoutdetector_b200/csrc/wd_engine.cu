@@ -848,15 +848,25 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     }
     const size_t smem = (size_t)2 * W * 3 + 48;
     if (smem > 48 * 1024) return fail(WD_ERR_INVALID, "frame width %d too large for the row staging buffer", W);
-    dim3 grid(224, n_out);
-    if (mode == WD_MODE_FP32_VALIDATE) {
-        a.pitch = 224;
-        a.pad = 0;
-        wd::preprocess_u8_kernel<float><<<grid, 224, smem, st>>>(a, static_cast<float*>(out));
-    } else {  // padded frames for the fused stem: image at columns kFramePad .. kFramePad+223, zeros around it
-        a.pitch = wd::kFramePitch;
-        a.pad = wd::kFramePad;
-        wd::preprocess_u8_kernel<__nv_bfloat16><<<grid, wd::kFramePitch, smem, st>>>(a, static_cast<__nv_bfloat16*>(out));
+    const bool f32 = mode == WD_MODE_FP32_VALIDATE;
+    // padded frames for the fused stem (bf16): image at columns kFramePad .. kFramePad+223, zeros around it
+    a.pitch = f32 ? 224 : wd::kFramePitch;
+    a.pad = f32 ? 0 : wd::kFramePad;
+    // rows of the source a band of kPreRows output rows can touch (+2 for the bilinear neighbour and rounding)
+    const size_t band_rows = (size_t)std::ceil(wd::kPreRows * a.scale_y) + 2;
+    const size_t smem_rows = band_rows * W * 3 + 48;
+    if (smem_rows <= 40 * 1024) {
+        dim3 grid(224 / wd::kPreRows, n_out);
+        if (f32)
+            wd::preprocess_u8_rows_kernel<float><<<grid, 256, smem_rows, st>>>(a, static_cast<float*>(out));
+        else
+            wd::preprocess_u8_rows_kernel<__nv_bfloat16><<<grid, 256, smem_rows, st>>>(a, static_cast<__nv_bfloat16*>(out));
+    } else {
+        dim3 grid(224, n_out);
+        if (f32)
+            wd::preprocess_u8_kernel<float><<<grid, 224, smem, st>>>(a, static_cast<float*>(out));
+        else
+            wd::preprocess_u8_kernel<__nv_bfloat16><<<grid, wd::kFramePitch, smem, st>>>(a, static_cast<__nv_bfloat16*>(out));
     }
     WD_CUDA(cudaGetLastError());
     return WD_OK;
