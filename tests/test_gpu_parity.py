@@ -212,6 +212,13 @@ CONV_CASES = [
     (2, 56, 64, 64, 3, 1, 0, 1, 0, "strip", 64),          # 4 strips per row, W resident
     (20, 28, 64, 256, 1, 1, 0, 1, 1, "tma", 256),         # W-resident 1x1 + residual ring across many tiles
     (20, 28, 64, 256, 1, 1, 0, 1, 1, "tma", 128),
+    (4, 28, 256, 64, 1, 1, 32, 1, 0, "tma", 64),          # fold 32 through TMA: k-block 0 = two SWIZZLE_64B halves (v4)
+    (3, 14, 256, 128, 1, 1, 32, 1, 0, "tma", 128),
+    (2, 28, 128, 128, 3, 2, 0, 1, 0, "tap", 128),         # tap mode (v4): 3x3 stride 2, 28 -> 14
+    (2, 28, 256, 512, 1, 2, 0, 0, 0, "tap", 256),         # 1x1 stride-2 downsample
+    (4, 14, 256, 256, 3, 2, 0, 1, 0, "tap", 256),         # 14 -> 7: two 7-pixel boxes per tile
+    (3, 7, 512, 512, 3, 1, 0, 1, 0, "tap", 256),          # 7x7 conv2, odd clip count: the last tile is half empty
+    (2, 56, 128, 128, 3, 2, 0, 1, 0, "tap", 128),         # 56 -> 28: two 14-pixel segments per row
 ]
 
 
@@ -223,6 +230,8 @@ def test_conv_umma_vs_torch(case, persistent):
     clips, H, Cin, Cout, k, stride, fold, relu, res, mode, tile_n = case
     if mode == "strip" and persistent < 2:
         pytest.skip("strip mode exists only in the v3/v4 kernels")
+    if (mode == "tap" or (mode == "tma" and fold == 32)) and persistent < 3:
+        pytest.skip("tap mode / fold-32 TMA exist only in the v4 kernel")
     g = torch.Generator().manual_seed(1000 + CONV_CASES.index(case))
     x = torch.randn(clips, H, H, 8, Cin, generator=g).to(torch.bfloat16).cuda()
     w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16).float()
@@ -292,7 +301,7 @@ def test_engine_bf16_ops_vs_bf16_emulation(engines, weights, use_tma):
         ref = O.tsm_forward(weights["rand"], x)
     e = engines("bf16", "rand", use_tma_a=use_tma)
     modes = {o["a_mode"] for o in e.ops()}
-    assert ("tma" in modes) == use_tma and "gather" in modes and "stem" in modes
+    assert ("tma" in modes) == use_tma and "gather" in modes and "stem" in modes and "tap" in modes
     frames = e.pack_nchw(x.cuda())
     _run_taps(e, frames, 2, taps, 2.5e-2)
     logits, probs, state = e.forward(frames)

@@ -36,9 +36,22 @@ constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SB
 __device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
     return (static_cast<uint64_t>(kDescHiSw128) << 32) | lo;
 }
+// K-major SWIZZLE_64B descriptor (64-byte rows: the fused stem, and the two 32-channel halves of a fold-32 k-block):
+// 8-row groups are 512 B apart.
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t umma_desc64_from_lo(uint32_t lo) {
+    return (static_cast<uint64_t>(kDescHiSw64) << 32) | lo;
+}
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
     return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
 }
+
+// A_TAP: 3x3 / 1x1 convolutions with stride 1 or 2 on 56/28/14/7-pixel rows that neither A_TMA nor A_STRIP covers
+// (stride-2 conv2 + downsample of layers 2-4, the 7x7 conv2 of layer 4).  The tile is 14 output pixels x 8 segments
+// (112 rows, like A_STRIP); every (tap, 64-channel block) k-block is ONE (two for 7-pixel rows) TMA box of a 5-D
+// view {C, T, W, H, clips} whose W / H dimensions are traversed with element stride = conv stride, start coordinate
+// ow0*stride + s - pad; padding is the out-of-bounds fill.  No per-element address arithmetic, no LSU traffic.
+enum AMode4 : int { A_TAP = 4 };
 
 // Debug timeline: role r of CTA 0 appends clock() samples to trace[r*2048 ...] (tools/trace_conv.py reads them).
 struct Tracer {
@@ -56,16 +69,19 @@ struct Tracer {
 // source of the TMA store: three 4 KiB slabs per warp, two residual chunks in flight per warp (64 KiB per SM).
 // Chosen per layer by the host (K >= 256: layers 3-4; the HBM-bound conv3 of layers 1-2 is faster with four warps).
 template <int AMODE, bool EPI8>
-constexpr int kThreadsFor = EPI8 ? 384 : (AMODE == A_TMA ? 224 : (AMODE == A_STRIP ? 288 : 320));
+constexpr int kThreadsFor = EPI8 ? 384 : ((AMODE == A_TMA || AMODE == A_TAP) ? 224 : (AMODE == A_STRIP ? 288 : 320));
 
 template <int BN, int AMODE, bool HAS_RES, bool EPI8 = false>
 __global__ void __launch_bounds__(kThreadsFor<AMODE, EPI8>, 1)
 conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
                const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap rmap,
-               const __grid_constant__ CUtensorMap omap16, const ConvArgs3 p) {
+               const __grid_constant__ CUtensorMap omap16, const __grid_constant__ CUtensorMap amap32,
+               const ConvArgs3 p) {
     constexpr int kBTile = BN * kTileK * 2;
     constexpr bool kStrip = (AMODE == A_STRIP);
-    constexpr bool kTmaA = (AMODE == A_TMA || AMODE == A_STRIP);
+    constexpr bool kTap = (AMODE == A_TAP);
+    constexpr bool k112 = kStrip || kTap;  // 112-row tiles (14 pixels x 8 segments)
+    constexpr bool kTmaA = (AMODE == A_TMA || AMODE == A_STRIP || AMODE == A_TAP);
     constexpr int kTaps = kStrip ? 9 : 1;  // W steps per A stage
     constexpr bool kEpi8 = EPI8;
     static_assert(!EPI8 || (AMODE == A_TMA && HAS_RES && BN >= 128), "8-warp epilogue: residual 1x1 TMA layers only");
@@ -84,7 +100,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     uint64_t* a_empty = bars + 8;             // [8]
     // A_TMA with streamed W: A and W of a k-block share ONE full / empty barrier pair, so the MMA issuer pays one
     // mbarrier round trip per k-block (tools/trace_conv.py: each try_wait costs it 270-560 cycles even when complete)
-    const bool merged = (AMODE == A_TMA) && !p.w_resident && p.a_stages == p.b_stages;
+    const bool merged = (AMODE == A_TMA || AMODE == A_TAP) && !p.w_resident && p.a_stages == p.b_stages;
     uint64_t* b_full = merged ? bars : bars + 16;        // [8]
     uint64_t* b_empty = merged ? bars + 8 : bars + 24;   // [8]
     uint64_t* tmem_full_bar = bars + 32;      // [2]
@@ -108,7 +124,8 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             tma_prefetch_desc(&omap);
             if (kTmaA) tma_prefetch_desc(&amap);
             if (HAS_RES) tma_prefetch_desc(&rmap);
-            if (kStrip) tma_prefetch_desc(&omap16);
+            if (k112) tma_prefetch_desc(&omap16);
+            if (AMODE == A_TMA && a.fold == 32) tma_prefetch_desc(&amap32);
             for (int s = 0; s < 8; ++s) {
                 mbar_init(&bars[s], merged ? 2 : (kStrip ? 3 : (kTmaA ? 1 : 128)));
                 mbar_init(&a_empty[s], 1);
@@ -149,6 +166,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             const int q = m_tile / p.tiles_w;  // n*H + h
             return (q * a.Wout + ws * kStripPixels) * 8;
         }
+        if (kTap) return m_tile * kStripRows;  // 14-pixel tiles are consecutive in the output row order
         return m_tile * kTileM;
     };
 
@@ -358,7 +376,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 if (warp == 0) etr.mark();  // e5: proxy fence done
                 if (elect_one()) {
                     // strip tiles have 112 rows: the last warp stores a 16-row box so it never touches the next strip
-                    if (kStrip && warp == 3)
+                    if (k112 && warp == 3)
                         tma_store_2d(&omap16, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
                     else
                         tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
@@ -449,10 +467,20 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                     const uint64_t adesc = umma_desc_from_lo(at_lo);
                     const uint64_t bdesc = umma_desc_from_lo(b_lo);
                     const uint32_t first = (as | tap) != 0 ? 1u : 0u;
+                    // fold 32 (Cin = 256): k-block 0 arrived as two 32-channel SWIZZLE_64B halves (t+1 / t-1 boxes)
+                    const bool split0 = (AMODE == A_TMA) && a.fold == 32 && as == 0;
                     if (elect_one()) {
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, first);
+                        if (split0) {
 #pragma unroll
-                        for (int k = 1; k < kTileK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_ss(d_tmem, umma_desc64_from_lo(at_lo + (k >> 1) * (8192 >> 4) + (k & 1) * 2),
+                                             bdesc + 2 * k, idesc, k ? 1u : first);
+                        } else {
+                            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, first);
+#pragma unroll
+                            for (int k = 1; k < kTileK / 16; ++k)
+                                umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                        }
                         if (!p.w_resident && !merged) umma_commit(&b_empty[bslot]);
                         if (tap == kTaps - 1) {
                             umma_commit(&a_empty[aslot]);
@@ -487,12 +515,27 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 step_h = sq % a.Hout;
                 step_n = sq / a.Hout;
             }
-            const int ahead = (!kStrip && p.prefetch_kblocks > 0) ? (p.prefetch_kblocks + a_steps - 1) / a_steps : 0;
+            const int ahead = (!k112 && p.prefetch_kblocks > 0) ? (p.prefetch_kblocks + a_steps - 1) / a_steps : 0;
             const int m_tiles_total = num_tiles / a.n_tiles;
             uint32_t it = 0;
             Tracer tr{(p.trace && blockIdx.x == 0 && warp == 6) ? p.trace + 2 * 2048 : nullptr, 0};
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int px0 = (m_tile * kTileM) >> 3;
+                // A_TAP: the tile is bh image rows of bw = 14 / bh pixels; row j is (clip nj, output row ohj, first pixel owj)
+                int tn[2] = {0, 0}, toh[2] = {0, 0}, tow = 0;
+                if (kTap) {
+                    const int bh = p.tap_bh;
+                    for (int j = 0; j < bh; ++j) {
+                        int q = m_tile * bh + j;              // output image-row index (or 14-pixel segment index)
+                        if (bh == 1) {
+                            tow = (q % p.tiles_w) * kStripPixels;
+                            q /= p.tiles_w;
+                        }
+                        toh[j] = q % a.Hout;
+                        tn[j] = q / a.Hout;
+                    }
+                }
+                int tap_r = 0, tap_s = 0, cb = 0;
                 for (int as = 0; as < a_steps; ++as, ++it) {
                     const int slot = it % p.a_stages;
                     tr.mark();
@@ -504,6 +547,16 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                         if (kStrip) {  // rows h-1, h, h+1; pixels w0-1 .. w0+14; OOB -> zeros (padding)
                             mbar_arrive_expect_tx(&a_full[slot], 16384);
                             tma_load_5d(&amap, &a_full[slot], dst + prow * 16384, c, 0, ws * kStripPixels - 1, h - 1 + prow, n);
+                        } else if (kTap) {
+                            mbar_arrive_expect_tx(&a_full[slot], kStripRows * 128);
+                            const int rows_per_box = kStripRows / p.tap_bh;
+                            for (int j = 0; j < p.tap_bh; ++j)
+                                tma_load_5d(&amap, &a_full[slot], dst + j * rows_per_box * 128, cb * kTileK, 0,
+                                            tow * a.stride + tap_s - a.pad, toh[j] * a.stride + tap_r - a.pad, tn[j]);
+                        } else if (a.fold == 32 && as == 0) {
+                            mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
+                            tma_load_3d(&amap32, &a_full[slot], dst, 0, 1, px0);          // channels 0..31 from t+1
+                            tma_load_3d(&amap32, &a_full[slot], dst + 8192, 32, -1, px0);  // channels 32..63 from t-1
                         } else {
                             int dt = 0;
                             if (a.fold) dt = (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
@@ -516,6 +569,13 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                         }
                     }
                     __syncwarp();
+                    if (kTap && ++cb == a.cin_blocks) {  // k-blocks are tap-major: (r, s, cin block)
+                        cb = 0;
+                        if (++tap_s == a.S) {
+                            tap_s = 0;
+                            ++tap_r;
+                        }
+                    }
                 }
                 m_tile += m_step;
                 if (kStrip) {

@@ -69,7 +69,8 @@ int get_encode_fn(EncodeTiledFn* out) {
 
 // bf16 tensor map, 128-byte swizzle. dims/strides innermost first; strides in bytes for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                   const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                   const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+                   const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn;
     WD_TRY(get_encode_fn(&fn));
     cuuint64_t gdim[5], gstr[5];
@@ -77,7 +78,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bdim[i] = box[i];
-        estr[i] = 1;
+        estr[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) gstr[i - 1] = strides[i - 1];
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
@@ -119,6 +120,7 @@ struct ConvLayer {
     CUtensorMap omap;  // output [rows, Cout], box {64, 32} (persistent kernel's TMA store)
     CUtensorMap rmap;  // residual, same geometry
     CUtensorMap omap16;  // output, box {64, 16}: last warp of a 112-row strip tile
+    CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
 };
 
 struct Op {
@@ -465,6 +467,8 @@ uint32_t* g_trace = nullptr;  // debug timeline buffer (WD_TRACE=<file> with the
 // engine-less single-layer hooks)
 int g_prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETCH_KBLOCKS")) : -1;  // -1 = per-layer rule
 
+int g_tap = getenv("WD_TAP") ? atoi(getenv("WD_TAP")) : 1;              // A_TAP mode for stride-2 / 7x7 convolutions
+int g_fold32_tma = getenv("WD_FOLD32") ? atoi(getenv("WD_FOLD32")) : 1;  // fold-32 conv1 through TMA (two SWIZZLE_64B halves)
 int g_epi8 = getenv("WD_EPI8") ? atoi(getenv("WD_EPI8")) : 1;  // 8-warp in-place epilogue for residual layers with K >= 256
 
 template <int BN, int AMODE, bool RES, bool EPI8 = false>
@@ -489,12 +493,14 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.off_out = sp.off_out;
     p.off_res = sp.off_res;
     p.off_bar = sp.off_bar;
-    p.tiles_w = AMODE == wd::A_STRIP ? a.Wout / wd::kStripPixels : 1;
+    p.tiles_w = (AMODE == wd::A_STRIP || AMODE == wd::A_TAP) ? std::max(1, a.Wout / wd::kStripPixels) : 1;
+    p.tap_bh = (AMODE == wd::A_TAP && a.Wout == 7) ? 2 : 1;
     // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
     p.prefetch_kblocks = (g_prefetch_kblocks >= 0) ? g_prefetch_kblocks : ((sp.a_stages <= 3 && a.kblocks >= 4) ? 4 : 0);
     p.trace = g_trace;
     const unsigned threads = wd::kThreadsFor<AMODE, EPI8>;
-    WD_CUDA(launch_pdl(kfn, (unsigned)grid, threads, (size_t)sp.total, st, c.wmap, c.amap, c.omap, c.rmap, c.omap16, p));
+    WD_CUDA(launch_pdl(kfn, (unsigned)grid, threads, (size_t)sp.total, st, c.wmap, c.amap, c.omap, c.rmap, c.omap16,
+                       c.amap32, p));
     return WD_OK;
 }
 
@@ -516,6 +522,9 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
         case wd::A_STRIP:
             if (!res) return launch_v4_t<BN, wd::A_STRIP, false>(c, a, sm_count, st);
             break;
+        case wd::A_TAP:
+            if (!res) return launch_v4_t<BN, wd::A_TAP, false>(c, a, sm_count, st);
+            break;
         case wd::A_GATHER:
             return res ? launch_v4_t<BN, wd::A_GATHER, true>(c, a, sm_count, st)
                        : launch_v4_t<BN, wd::A_GATHER, false>(c, a, sm_count, st);
@@ -525,6 +534,7 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
 
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
     if (c.a_mode == wd::A_STRIP) a.num_tiles = (a.M / wd::kStripRows) * a.n_tiles;  // tiles are 14-pixel row segments
+    if (c.a_mode == wd::A_TAP) a.num_tiles = ((a.M + wd::kStripRows - 1) / wd::kStripRows) * a.n_tiles;
     switch (c.tile_n) {
         case 64: return launch_v4_bn<64>(c, a, sm_count, st);
         case 128: return launch_v4_bn<128>(c, a, sm_count, st);
@@ -590,7 +600,7 @@ wd::ConvArgs conv_args(const ConvLayer& c, const void* in, void* out, const void
 // Fold BN into (w, bias) on the host and upload in the layout of the engine's mode.
 //   w: [Cout, Cin, k, k] fp32; scale/shift: [Cout]
 int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const float* w, const float* scale,
-                const float* shift, int use_strip = 0) {
+                const float* shift, int use_strip = 0, int v4 = 0) {
     const int K = c.Cin * c.k * c.k;
     if (c.w_packed) cudaFree(c.w_packed);
     if (c.bias) cudaFree(c.bias);
@@ -644,10 +654,14 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
         return fail(WD_ERR_INVALID, "%s: Cout=%d not divisible by tile %d", c.name.c_str(), c.Cout, c.tile_n);
     if (c.stem)
         c.a_mode = wd::A_STEM;
-    else if (use_tma_a && c.k == 1 && c.stride == 1 && (c.fold == 0 || c.fold % 64 == 0))
+    else if (use_tma_a && c.k == 1 && c.stride == 1 && (c.fold == 0 || c.fold % 64 == 0 || (c.fold == 32 && g_fold32_tma && v4)))
         c.a_mode = wd::A_TMA;
     else if (use_strip && c.k == 3 && c.stride == 1 && c.Wout % wd::kStripPixels == 0 && c.Wout >= wd::kStripPixels)
         c.a_mode = wd::A_STRIP;
+    else if (use_strip && v4 && g_tap && c.fold == 0 && (c.k == 3 || c.stride == 2) &&
+             (c.Wout % wd::kStripPixels == 0 || (c.Wout == 7 && g_tap >= 2)))
+        c.a_mode = wd::A_TAP;  // stride-2 convolutions: one TMA box per (tap, channel block).  7-pixel rows (two boxes per
+                               // tile, 12.5 % dead rows) measured slower than the cp.async gather: opt-in (WD_TAP=2)
     else
         c.a_mode = wd::A_GATHER;
     WD_CUDA(cudaMalloc(&c.w_packed, p.size() * 2));
@@ -679,6 +693,25 @@ int make_amap5(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t
                                  (uint64_t)H * W * Cin * 16};
     const uint32_t box[5] = {64, 8, 16, 1, 1};
     return make_tmap_bf16(map, base, 5, dims, strides, box);
+}
+
+// A_TAP: 5-D view {C, T=8, W, H, clips}; W and H are traversed with element stride = conv stride, the box covers
+// `bw` output pixels of one image row (14, or 7 for 7-pixel rows: two boxes per tile).
+int make_amap_tap(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t clips, int stride, int bw) {
+    const uint64_t dims[5] = {(uint64_t)Cin, 8, (uint64_t)W, (uint64_t)H, (uint64_t)clips};
+    const uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16, (uint64_t)W * Cin * 16,
+                                 (uint64_t)H * W * Cin * 16};
+    const uint32_t box[5] = {64, 8, (uint32_t)((bw - 1) * stride + 1), 1, 1};
+    const uint32_t es[5] = {1, 1, (uint32_t)stride, 1, 1};
+    return make_tmap_bf16(map, base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
+}
+
+// fold 32: 32-channel boxes {32, 8, 16} of the {C, T, P} view, 64-byte rows with SWIZZLE_64B.
+int make_amap32(CUtensorMap* map, const void* base, int Cin, size_t pixels) {
+    const uint64_t dims[3] = {(uint64_t)Cin, 8, (uint64_t)pixels};
+    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16};
+    const uint32_t box[3] = {32, 8, 16};
+    return make_tmap_bf16(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 // 3-D activation view {C, T=8, P} of a T-inner buffer for the A_TMA mode.
@@ -1004,7 +1037,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             shift[i] = b[i] - mu[i] * s;
         }
         WD_TRY(upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, w, scale.data(), shift.data(),
-                           e->persistent >= 2 ? e->use_strip : 0));
+                           e->persistent >= 2 ? e->use_strip : 0, e->persistent >= 3));
     }
     // A-operand TMA views over the workspace buffers
     if (e->desc.mode == WD_MODE_BF16) {
@@ -1018,8 +1051,15 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
                 WD_TRY(make_amap5(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
             }
+            if (c.a_mode == wd::A_TAP) {
+                WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
+                WD_TRY(make_amap_tap(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips, c.stride,
+                                     c.Wout == 7 ? 7 : wd::kStripPixels));
+            }
             if (c.a_mode != wd::A_TMA) continue;
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
+            if (c.fold == 32)
+                WD_TRY(make_amap32(&c.amap32, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
         }
     }
     const float *fw, *fb;
@@ -1237,13 +1277,20 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
     c.relu = relu;
     std::vector<float> ones(Cout, 1.0f);
     WD_TRY(upload_conv(c, WD_MODE_BF16, tile_n, a_mode == wd::A_TMA ? 1 : 0, w, ones.data(), bias,
-                       a_mode == wd::A_STRIP ? 1 : 0));
+                       (a_mode == wd::A_STRIP || a_mode == wd::A_TAP) ? 1 : 0, persistent >= 3));
+    // the test hook may force tap mode on every shape the kernel supports (strip-eligible and 7-pixel rows included)
+    if (a_mode == wd::A_TAP && persistent >= 3 && fold == 0 && (c.Wout % wd::kStripPixels == 0 || c.Wout == 7)) c.a_mode = wd::A_TAP;
     int rc = WD_OK;
-    if ((a_mode == wd::A_TMA || a_mode == wd::A_STRIP) && c.a_mode != a_mode) {
+    if ((a_mode == wd::A_TMA || a_mode == wd::A_STRIP || a_mode == wd::A_TAP) && c.a_mode != a_mode) {
         rc = fail(WD_ERR_INVALID, "shape not eligible for the requested A-operand path");
     } else {
-        if (a_mode != wd::A_TMA && a_mode != wd::A_STRIP) c.a_mode = wd::A_GATHER;
+        if (a_mode != wd::A_TMA && a_mode != wd::A_STRIP && a_mode != wd::A_TAP) c.a_mode = wd::A_GATHER;
         if (c.a_mode == wd::A_TMA) rc = make_amap(&c.amap, x, Cin, (size_t)clips * Hin * Win);
+        if (c.a_mode == wd::A_TMA && fold == 32 && rc == WD_OK) rc = make_amap32(&c.amap32, x, Cin, (size_t)clips * Hin * Win);
+        if (c.a_mode == wd::A_TAP) {
+            rc = make_amap_tap(&c.amap, x, Cin, Win, Hin, (size_t)clips, stride, c.Wout == 7 ? 7 : wd::kStripPixels);
+            if (rc == WD_OK) rc = make_omap(&c.omap16, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 16);
+        }
         if (c.a_mode == wd::A_STRIP) {
             rc = make_amap5(&c.amap, x, Cin, Win, Hin, (size_t)clips);
             if (rc == WD_OK) rc = make_omap(&c.omap16, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 16);

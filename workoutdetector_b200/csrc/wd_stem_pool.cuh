@@ -54,11 +54,6 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     return d;
 }
 
-// K-major SWIZZLE_64B descriptor: 8-row groups are 512 B apart.
-constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
-__device__ __forceinline__ uint64_t umma_desc64_from_lo(uint32_t lo) {
-    return (static_cast<uint64_t>(kDescHiSw64) << 32) | lo;
-}
 
 __global__ void __launch_bounds__(192, 1)
 stem_pool_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,

@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import MODE_BF16, MODE_FP32_VALIDATE, ModelDesc, NamedTensor, check
 
 OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head", 4: "stem_pool"}
-A_MODES = {0: "gather", 1: "stem", 2: "tma", 3: "strip", -1: "-"}
+A_MODES = {0: "gather", 1: "stem", 2: "tma", 3: "strip", 4: "tap", -1: "-"}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -226,7 +226,7 @@ def debug_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: O
     bc = bias.detach().to("cpu", torch.float32).contiguous()
     torch.cuda.synchronize()
     check(lib.wd_debug_conv(_ptr(x), _ptr(wc), _ptr(bc), _ptr(residual), _ptr(y), clips, Hin, Win, Cin, Cout, k,
-                            stride, fold, int(relu), {"gather": 0, "tma": 2, "strip": 3}[a_mode], tile_n, int(persistent)))
+                            stride, fold, int(relu), {"gather": 0, "tma": 2, "strip": 3, "tap": 4}[a_mode], tile_n, int(persistent)))
     return y
 
 
@@ -243,5 +243,5 @@ def bench_conv(clips: int, H: int, Cin: int, Cout: int, k: int, stride: int, fol
     ms = C.c_float()
     torch.cuda.synchronize()
     check(lib.wd_bench_conv(_ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), clips, H, H, Cin, Cout, k, stride, fold, 1,
-                            {"gather": 0, "tma": 2, "strip": 3}[a_mode], tile_n, int(persistent), iters, C.byref(ms)))
+                            {"gather": 0, "tma": 2, "strip": 3, "tap": 4}[a_mode], tile_n, int(persistent), iters, C.byref(ms)))
     return ms.value
