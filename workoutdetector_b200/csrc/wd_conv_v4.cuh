@@ -399,22 +399,29 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             }
             __syncwarp();
         } else {
-            uint32_t it = 0;
+            // W stages are groups of p.w_group consecutive (A stage, tap) steps: with narrow tiles one step is only
+            // 128-256 tensor cycles, far less than the ~600 cycles an mbarrier round trip costs the MMA issuer
+            // (tools/trace_conv.py), so the issuer waits once per group.
+            const int g = p.w_group;
+            const int steps = a_steps * kTaps;
+            uint32_t grp = 0;
             Tracer tr{(p.trace && blockIdx.x == 0) ? p.trace + 1 * 2048 : nullptr, 0};
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int as = 0; as < a_steps; ++as) {
-                    for (int tap = 0; tap < kTaps; ++tap, ++it) {
-                        const int slot = it % p.b_stages;
-                        tr.mark();
-                        mbar_wait(&b_empty[slot], ((it / p.b_stages) & 1) ^ 1);
-                        tr.mark();
-                        const int kbi = kStrip ? tap * a.cin_blocks + as : as;
-                        if (elect_one()) {
-                            mbar_arrive_expect_tx(&b_full[slot], kBTile);
-                            tma_load_2d(&wmap, &b_full[slot], sB + slot * kBTile, kbi * kTileK, cta_n0);
+                for (int j0 = 0; j0 < steps; j0 += g, ++grp) {
+                    const int slot = grp % p.b_stages;
+                    tr.mark();
+                    mbar_wait(&b_empty[slot], ((grp / p.b_stages) & 1) ^ 1);
+                    tr.mark();
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&b_full[slot], (uint32_t)g * kBTile);
+                        for (int q = 0; q < g; ++q) {
+                            const int j = j0 + q;
+                            const int as = j / kTaps, tap = j - as * kTaps;
+                            const int kbi = kStrip ? tap * a.cin_blocks + as : as;
+                            tma_load_2d(&wmap, &b_full[slot], sB + (slot * g + q) * kBTile, kbi * kTileK, cta_n0);
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -447,6 +454,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 for (int tap = 0; tap < kTaps; ++tap) {
                     uint32_t b_lo;
                     int bslot = 0;
+                    bool b_last = true;
                     const int kbi = kStrip ? tap * a.cin_blocks + as : as;
                     if (p.w_resident) {
                         b_lo = sB_lo + ((uint32_t)(kbi * kBTile) >> 4);
@@ -454,11 +462,15 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                         bslot = aslot;
                         b_lo = sB_lo + ((uint32_t)(bslot * kBTile) >> 4);
                     } else {
-                        bslot = itb % p.b_stages;
-                        mbar_wait(&b_full[bslot], (itb / p.b_stages) & 1);
-                        tr.mark();
-                        tc_fence_after_sync();
-                        b_lo = sB_lo + ((uint32_t)(bslot * kBTile) >> 4);
+                        const uint32_t grp = itb / (uint32_t)p.w_group, within = itb % (uint32_t)p.w_group;
+                        bslot = grp % p.b_stages;
+                        if (within == 0) {
+                            mbar_wait(&b_full[bslot], (grp / p.b_stages) & 1);
+                            tr.mark();
+                            tc_fence_after_sync();
+                        }
+                        b_lo = sB_lo + ((uint32_t)((bslot * p.w_group + within) * kBTile) >> 4);
+                        b_last = (within == (uint32_t)p.w_group - 1);
                         ++itb;
                     }
                     // strip: tap (r, s) = row slot r, shifted by s pixels (one pixel = one 1024-byte atom)
@@ -481,7 +493,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                             for (int k = 1; k < kTileK / 16; ++k)
                                 umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                         }
-                        if (!p.w_resident && !merged) umma_commit(&b_empty[bslot]);
+                        if (!p.w_resident && !merged && b_last) umma_commit(&b_empty[bslot]);
                         if (tap == kTaps - 1) {
                             umma_commit(&a_empty[aslot]);
                             if (as == a_steps - 1) umma_commit(&tmem_full_bar[acc]);

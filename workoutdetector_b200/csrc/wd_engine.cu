@@ -469,6 +469,7 @@ int g_prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETC
 
 int g_tap = getenv("WD_TAP") ? atoi(getenv("WD_TAP")) : 1;              // A_TAP mode for stride-2 / 7x7 convolutions
 int g_fold32_tma = getenv("WD_FOLD32") ? atoi(getenv("WD_FOLD32")) : 1;  // fold-32 conv1 through TMA (two SWIZZLE_64B halves)
+int g_w_group = getenv("WD_WGROUP") ? atoi(getenv("WD_WGROUP")) : 1;    // group W steps of narrow strip tiles
 int g_epi8 = getenv("WD_EPI8") ? atoi(getenv("WD_EPI8")) : 1;  // 8-warp in-place epilogue for residual layers with K >= 256
 
 template <int BN, int AMODE, bool RES, bool EPI8 = false>
@@ -493,6 +494,15 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.off_out = sp.off_out;
     p.off_res = sp.off_res;
     p.off_bar = sp.off_bar;
+    // narrow tiles: group W steps so that one W stage carries >= 512 tensor cycles (strip mode, streamed W)
+    p.w_group = 1;
+    if (AMODE == wd::A_STRIP && !sp.w_resident && g_w_group) {
+        const int steps = 9 * a.cin_blocks, want = 256 / BN;
+        if (want > 1 && steps % want == 0 && sp.b_stages / want >= 2) {
+            p.w_group = want;
+            p.b_stages = sp.b_stages / want;
+        }
+    }
     p.tiles_w = (AMODE == wd::A_STRIP || AMODE == wd::A_TAP) ? std::max(1, a.Wout / wd::kStripPixels) : 1;
     p.tap_bh = (AMODE == wd::A_TAP && a.Wout == 7) ? 2 : 1;
     // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
