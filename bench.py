@@ -236,15 +236,19 @@ def main():
     conv_flops = sum(2.0 * o["macs_per_clip"] * B for o in ops if o["kind"] in ("conv", "stem", "stem_pool"))
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")   # dram bytes per step from the ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")   # dram bytes of the same launches from the ncu pass
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_step")
+    # "launch" here = the 53 tcgen05 launches of one step taken together (52 x conv_v4_kernel + stem_pool_kernel):
+    # achieved = their algorithmic FLOPs / the sum of their CUDA-event durations; traffic = their summed DRAM bytes.
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["sustained"], traffic=traffic,
-                    kernel="conv_v4_kernel x52 + stem_pool_kernel (all tcgen05 launches of a step, aggregated)",
+                    kernel="conv_v4_kernel (52 launches) + stem_pool_kernel (1) per step, aggregated",
                     frac_of_burst=achieved / peaks["burst"], peak_source=peaks["source"],
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / max(sum(op_ms), 1e-9),
+                    dram_gbs=(traffic / (conv_ms * 1e-3) / 1e9) if traffic else None,
+                    dram_frac_of_hbm_peak=(traffic / (conv_ms * 1e-3) / 1e9 / peaks["hbm"]) if traffic else None,
                     whole_step_tflops=value / world * GFLOP_PER_CLIP / 1e3,
                     whole_step_frac=value / world * GFLOP_PER_CLIP / 1e3 / peaks["sustained"])
 
