@@ -1,0 +1,318 @@
+// wd_conv_2cta.cuh — CTA-pair (cta_group::2) version of the 1x1 stride-1 convolution for the compute-bound layers
+// (conv1 of the layer-3/4 bottlenecks: Cout tile 256, K >= 256, no residual).
+//
+// Why: tools/trace_conv.py + profiles/r01_ncu_step_batch64.txt show these layers at ~690 cycles per k-block against
+// 512 tensor cycles.  Shared memory moves 128 B/clk and has to carry the tensor core's operand reads (SS mode re-reads
+// A and W for every MMA: 12 KiB per 128x256x16) AND the TMA fills (another 12 KiB per MMA for a streamed 128x256 tile).
+// With tcgen05.mma.cta_group::2 a pair of CTAs on one TPC computes a 256x256 tile: each CTA keeps its own 128 rows
+// of A and only HALF of the W tile (128 of the 256 output channels); the tensor cores of both SMs read both halves.
+// Per SM and MMA the W fill and the W read halve (24 KiB -> 16 KiB of smem traffic), and a stage is 32 KiB instead of
+// 48 KiB, so the ring is 5 deep instead of 4.
+//
+// Protocol (same roles as conv_v4_kernel; rank = %cluster_ctarank, rank 0 is the leader):
+//   full[s]   (leader's)  4 arrivals: leader A / W producers arrive.expect_tx(bytes of BOTH CTAs), peer producers
+//                         arrive remotely; every TMA load (cta_group::2) signals the leader's barrier
+//   empty[s]  (own)       tcgen05.commit.cta_group::2 ... multicast to both CTAs
+//   tmem_full[a] (own)    multicast commit after the last k-block of a tile
+//   tmem_empty[a] (leader's) 16 arrivals: the eight epilogue warps of both CTAs (remote arrive for the peer)
+// Only the leader's warp 5 issues MMAs; TMEM is allocated with cta_group::2 by warp 5 of both CTAs.
+#pragma once
+#include "wd_conv_v4.cuh"
+
+namespace wd {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr`'s counterpart in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                                 int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T, 256 x N x 16
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+constexpr int k2cStage = kATileBytes + 128 * kTileK * 2;  // A 16 KiB + half of the 256-row W tile 16 KiB
+constexpr int k2cStages = 5;
+constexpr int k2cOffOut = k2cStages * k2cStage;            // 8 warps x 2 x 4 KiB output slabs
+constexpr int k2cOffBar = k2cOffOut + 16 * kEpiSlab;
+constexpr int k2cSmem = k2cOffBar + 2048 + 1024;
+
+struct Conv2CtaArgs {
+    const float* bias;  // [Cout]
+    int M;              // output rows
+    int kblocks;        // Cin / 64
+    int fold;           // TemporalShift fold (multiple of 64) or 0
+    int relu;
+    int n_tiles;        // Cout / 256
+    int num_tiles;      // ceil(M / 256) * n_tiles; the number of pairs is a multiple of n_tiles
+    uint32_t* trace;    // debug timeline (CTA 0), see Tracer
+    int prefetch;       // L2-prefetch distance of the A operand in k-blocks (0 = off)
+};
+
+__global__ void __launch_bounds__(384, 1)
+conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_constant__ CUtensorMap amap,
+                 const __grid_constant__ CUtensorMap omap, const Conv2CtaArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sOut = smem + k2cOffOut;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2cOffBar);
+    uint64_t* full = bars;                 // [k2cStages]   (the leader's are used)
+    uint64_t* empty = bars + 8;            // [k2cStages]
+    uint64_t* tmem_full_bar = bars + 16;   // [2]
+    uint64_t* tmem_empty_bar = bars + 18;  // [2]           (the leader's are used)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
+    float* sBias = reinterpret_cast<float*>(bars + 32);  // 256 floats
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x >> 1;
+    const int npairs = (int)gridDim.x >> 1;
+    const int cta_n0 = (pair % a.n_tiles) * 256;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&wmap128);
+            tma_prefetch_desc(&amap);
+            tma_prefetch_desc(&omap);
+            for (int s = 0; s < k2cStages; ++s) {
+                mbar_init(&full[s], 4);
+                mbar_init(&empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 16);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 5) {
+        tmem_alloc_2cta(tmem_ptr, 512);
+        tmem_relinquish_2cta();
+    }
+    if (warp < 4)
+        for (int i = tid; i < 256; i += 128) sBias[i] = a.bias[cta_n0 + i];  // warps 0-3 = threads 0..127
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
+
+    if (warp < 4 || warp >= 8) {
+        // ==========================================================================================
+        // Epilogue: this CTA's 128 rows x 256 columns, eight warps (with 256 x 256 pair tiles the MMA of a tile is
+        // about as long as a four-warp epilogue; two warps per scheduler overlap each other's issue latencies)
+        // ==========================================================================================
+        const int quarter = warp & 3, half = warp >> 3;
+        uint8_t* my_out = sOut + (half * 4 + quarter) * 2 * kEpiSlab;
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        const bool relu = a.relu != 0;
+        uint32_t chunk_idx = 0;
+        int tile_iter = 0;
+        for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
+            const int mrow = (tile / a.n_tiles) * 256 + (int)rank * 128 + quarter * 32;
+            const int acc = tile_iter & 1;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+            const uint32_t leader_empty = mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0);
+            mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 2 * half; c < 2 * half + 2; ++c, ++chunk_idx) {
+                float4 bb[16];
+                const float4* bsrc = reinterpret_cast<const float4*>(sBias + c * 64);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * 64, v0);
+                tmem_ld32(taddr + c * 64 + 32, v1);
+                tmem_ld_wait();
+                if (c == 2 * half + 1) {  // this warp's share is drained: tell the leader's MMA issuer
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive_cluster(leader_empty);
+                    __syncwarp();
+                }
+                if (elect_one()) tma_store_wait_read1();
+                __syncwarp();
+                uint8_t* obuf = my_out + (chunk_idx & 1) * kEpiSlab + row_off;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t* v = (u < 4) ? (v0 + u * 8) : (v1 + (u - 4) * 8);
+                    const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    uint32_t o[4];
+                    if (relu) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2_relu(f[2 * q], f[2 * q + 1]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp == 4 || warp == 6) {
+        // ==========================================================================================
+        // Producers (both CTAs): warp 4 = this CTA's half of W, warp 6 = this CTA's 128 rows of A
+        // ==========================================================================================
+        const bool is_w = (warp == 4);
+        uint32_t it = 0;
+        Tracer tr{(a.trace && blockIdx.x == 0) ? a.trace + (is_w ? 1 : 2) * 2048 : nullptr, 0};
+        for (int tile = pair; tile < a.num_tiles; tile += npairs) {
+            const int px0 = ((tile / a.n_tiles) * 256 + (int)rank * 128) >> 3;
+            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                const int slot = it % k2cStages;
+                tr.mark();
+                mbar_wait(&empty[slot], ((it / k2cStages) & 1) ^ 1);
+                tr.mark();
+                const uint32_t leader_full = mapa_shared(smem_u32(&full[slot]), 0);
+                uint8_t* stage = smem + slot * k2cStage;
+                if (elect_one()) {
+                    // the leader announces the bytes of both CTAs for its operand, the peer just arrives
+                    if (rank == 0) mbar_arrive_expect_tx_cluster(leader_full, 2 * 16384);
+                    else mbar_arrive_cluster(leader_full);
+                    if (is_w) {
+                        tma_load_2d_2cta(&wmap128, leader_full, stage + kATileBytes, kb * kTileK, cta_n0 + (int)rank * 128);
+                    } else {
+                        const int c = kb * kTileK;
+                        int dt = 0;
+                        if (a.fold) dt = (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
+                        tma_load_3d_2cta(&amap, leader_full, stage, c, dt, px0);
+                        // Optional L2 prefetch of the A box `prefetch` k-blocks ahead.  Measured: no gain — with A
+                        // forced L2-resident this kernel runs at 1336 TFLOP/s, with A from HBM at 1040: the layer
+                        // sits on the HBM roofline (205 MB in + 51 MB out in 50 us), not on HBM latency.
+                        if (a.prefetch > 0) {
+                            const int kq = kb + a.prefetch;
+                            const int t2 = tile + (kq / a.kblocks) * npairs;
+                            if (t2 < a.num_tiles) {
+                                const int c2 = (kq % a.kblocks) * kTileK;
+                                int dt2 = 0;
+                                if (a.fold) dt2 = (c2 < a.fold) ? 1 : ((c2 < 2 * a.fold) ? -1 : 0);
+                                tma_prefetch_l2_3d(&amap, c2, dt2, ((t2 / a.n_tiles) * 256 + (int)rank * 128) >> 3);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 5 && rank == 0) {
+        // ==========================================================================================
+        // MMA issuer (leader CTA only): 256 x 256 x 16 per instruction
+        // ==========================================================================================
+        constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+        const uint32_t s_lo = umma_desc_lo(smem_u32(smem));
+        uint32_t it = 0;
+        int tile_iter = 0;
+        Tracer tr{(a.trace && blockIdx.x == 0) ? a.trace : nullptr, 0};
+        for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
+            const int acc = tile_iter & 1;
+            tr.mark();
+            mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                const int slot = it % k2cStages;
+                tr.mark();
+                mbar_wait(&full[slot], (it / k2cStages) & 1);
+                tr.mark();
+                tc_fence_after_sync();
+                const uint32_t a_lo = s_lo + ((uint32_t)(slot * k2cStage) >> 4);
+                const uint32_t b_lo = a_lo + (kATileBytes >> 4);
+                const uint64_t adesc = umma_desc_from_lo(a_lo);
+                const uint64_t bdesc = umma_desc_from_lo(b_lo);
+                if (elect_one()) {
+                    umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 1; k < kTileK / 16; ++k) umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                    umma_commit_2cta(&empty[slot]);
+                    if (kb == a.kblocks - 1) umma_commit_2cta(&tmem_full_bar[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();  // the peer may still be arriving on / reading from this CTA's shared memory and TMEM
+    if (warp == 5) tmem_dealloc_2cta(tmem_base, 512);
+}
+
+}  // namespace wd

@@ -19,6 +19,7 @@
 #include "wd_conv_umma.cuh"
 #include "wd_conv_v3.cuh"
 #include "wd_conv_v4.cuh"
+#include "wd_conv_2cta.cuh"
 #include "wd_stem_pool.cuh"
 
 namespace {
@@ -120,6 +121,7 @@ struct ConvLayer {
     CUtensorMap omap;  // output [rows, Cout], box {64, 32} (persistent kernel's TMA store)
     CUtensorMap rmap;  // residual, same geometry
     CUtensorMap omap16;  // output, box {64, 16}: last warp of a 112-row strip tile
+    CUtensorMap wmap128; // W [Cout, K], box {64, 128}: one CTA's half of a 256-channel tile (cta_group::2 kernel)
     CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
 };
 
@@ -542,7 +544,52 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
     return fail(WD_ERR_INVALID, "no v4 conv kernel for tile_n=%d a_mode=%d residual=%d", c.tile_n, c.a_mode, (int)res);
 }
 
+int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 1;  // cta_group::2 kernel for compute-bound 1x1 layers
+
+// CTA-pair kernel (wd_conv_2cta.cuh): 1x1 stride-1, no residual, 256-wide Cout tiles, K >= 256.
+bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
+    return g_2cta && c.a_mode == wd::A_TMA && c.tile_n == 256 && a.residual == nullptr && a.kblocks >= 4 &&
+           (a.fold == 0 || a.fold % 64 == 0) && c.Cout % 256 == 0;
+}
+
+int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(wd::conv_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::k2cSmem));
+        configured = true;
+    }
+    wd::Conv2CtaArgs p{};
+    p.bias = a.bias;
+    p.M = a.M;
+    p.kblocks = a.kblocks;
+    p.fold = a.fold;
+    p.relu = a.relu;
+    p.n_tiles = c.Cout / 256;
+    p.num_tiles = ((a.M + 255) / 256) * p.n_tiles;
+    p.trace = g_trace;
+    p.prefetch = g_prefetch_kblocks >= 0 ? g_prefetch_kblocks : 0;
+    int pairs = std::min(p.num_tiles, sm_count / 2);
+    pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);  // a pair keeps one n-tile (bias)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = wd::k2cSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    WD_CUDA(cudaLaunchKernelEx(&cfg, wd::conv_2cta_kernel, c.wmap128, c.amap, c.omap, p));
+    return WD_OK;
+}
+
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    if (eligible_2cta(c, a)) return launch_2cta(c, a, sm_count, st);
     if (c.a_mode == wd::A_STRIP) a.num_tiles = (a.M / wd::kStripRows) * a.n_tiles;  // tiles are 14-pixel row segments
     if (c.a_mode == wd::A_TAP) a.num_tiles = ((a.M + wd::kStripRows - 1) / wd::kStripRows) * a.n_tiles;
     switch (c.tile_n) {
@@ -685,6 +732,10 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     }
     const uint32_t box[2] = {64, (uint32_t)c.tile_n};
     WD_TRY(make_tmap_bf16(&c.wmap, c.w_packed, 2, dims, strides, box));
+    if (c.Cout % 256 == 0) {
+        const uint32_t box128[2] = {64, 128};
+        WD_TRY(make_tmap_bf16(&c.wmap128, c.w_packed, 2, dims, strides, box128));
+    }
     return WD_OK;
 }
 
@@ -994,6 +1045,8 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     } else if (!strcmp(key, "persistent")) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
+    } else if (!strcmp(key, "use_2cta")) {
+        g_2cta = value ? 1 : 0;
     } else if (!strcmp(key, "pdl")) {
         g_pdl = value ? 1 : 0;
     } else if (!strcmp(key, "prefetch_kblocks")) {
