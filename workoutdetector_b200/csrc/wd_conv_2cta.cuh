@@ -58,6 +58,16 @@ __device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* map, uint32_
         : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_2cta(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                  : "memory");
@@ -313,6 +323,262 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
     __syncthreads();
     cluster_sync_all();  // the peer may still be arriving on / reading from this CTA's shared memory and TMEM
     if (warp == 5) tmem_dealloc_2cta(tmem_base, 512);
+}
+
+
+
+// ==================================================================================================
+// CTA-pair version of the A_STRIP mode (3x3 stride-1 convolutions of layers 2 and 3; see wd_conv_v3.cuh for the
+// strip trick).  A pair tile is two 14-pixel strips (consecutive strip indices), one per CTA; every tap's W tile is
+// split between the two CTAs (BN/2 output channels each) and read by both tensor cores.  Same barrier protocol as
+// conv_2cta_kernel, with a separate W ring:
+//   a_full[s] (leader's)  6 arrivals: the three row producers of both CTAs (each announces its own 16 KiB)
+//   w_full[s] (leader's)  2 arrivals: leader W producer (bytes of both halves) + remote arrive of the peer's
+//   a_empty / w_empty / tmem_full (own): multicast commits;  tmem_empty (leader's): 8 arrivals
+// Warp roles (288 threads): 0-3 epilogue, 4 W producer, 5 MMA issuer (leader only) + TMEM, 6-8 A row producers.
+// ==================================================================================================
+struct Conv2CtaStripArgs {
+    const float* bias;
+    int Hout, Wout;    // = Hin, Win
+    int cin_blocks;    // Cin / 64
+    int relu;
+    int n_tiles;       // Cout / BN
+    int num_tiles;     // ceil(strips / 2) * n_tiles
+    int num_strips;    // clips * H * (W / 14)
+    int tiles_w;       // W / 14
+    int w_stages;      // W ring depth
+    int off_w, off_out, off_bar;  // byte offsets (A ring of two kStripStage stages at 0)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(288, 1)
+conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __grid_constant__ CUtensorMap amap,
+                       const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
+                       const Conv2CtaStripArgs a) {
+    constexpr int kWHalf = (BN / 2) * kTileK * 2;  // this CTA's half of one tap's W tile
+    constexpr int kAStages = 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + a.off_w;
+    uint8_t* sOut = smem + a.off_out;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+    uint64_t* a_full = bars;               // [2]  (leader's)
+    uint64_t* a_empty = bars + 2;          // [2]
+    uint64_t* w_full = bars + 8;           // [8]  (leader's)
+    uint64_t* w_empty = bars + 16;         // [8]
+    uint64_t* tmem_full_bar = bars + 24;   // [2]
+    uint64_t* tmem_empty_bar = bars + 26;  // [2]  (leader's)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 28);
+    float* sBias = reinterpret_cast<float*>(bars + 32);  // BN floats
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x >> 1;
+    const int npairs = (int)gridDim.x >> 1;
+    const int cta_n0 = (pair % a.n_tiles) * BN;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&wmap_half);
+            tma_prefetch_desc(&amap);
+            tma_prefetch_desc(&omap);
+            tma_prefetch_desc(&omap16);
+            for (int s = 0; s < kAStages; ++s) {
+                mbar_init(&a_full[s], 6);
+                mbar_init(&a_empty[s], 1);
+            }
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(&w_full[s], 2);
+                mbar_init(&w_empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 8);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 5) {
+        tmem_alloc_2cta(tmem_ptr, 2 * BN);
+        tmem_relinquish_2cta();
+    }
+    if (warp < 4)
+        for (int i = tid; i < BN; i += 128) sBias[i] = a.bias[cta_n0 + i];
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
+
+    // this CTA's strip of pair tile `tile` (may be past the end for the peer of the last tile: loads are zero-filled
+    // by TMA, stores are skipped)
+    auto strip_of = [&](int tile) { return (tile / a.n_tiles) * 2 + (int)rank; };
+
+    if (warp < 4) {
+        // ============================== epilogue: 112 rows x BN columns ==============================
+        uint8_t* my_out = sOut + warp * 2 * kEpiSlab;
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        constexpr int kChunks = BN / 64;
+        const bool relu = a.relu != 0;
+        uint32_t chunk_idx = 0;
+        int tile_iter = 0;
+        for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
+            const int strip = strip_of(tile);
+            const bool live = strip < a.num_strips;
+            const int mrow = strip * kStripRows + warp * 32;  // strips are consecutive 112-row groups of the output
+            const int acc = tile_iter & 1;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN;
+            const uint32_t leader_empty = mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0);
+            mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c, ++chunk_idx) {
+                float4 bb[16];
+                const float4* bsrc = reinterpret_cast<const float4*>(sBias + c * 64);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * 64, v0);
+                tmem_ld32(taddr + c * 64 + 32, v1);
+                tmem_ld_wait();
+                if (c == kChunks - 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive_cluster(leader_empty);
+                    __syncwarp();
+                }
+                if (elect_one()) tma_store_wait_read1();
+                __syncwarp();
+                uint8_t* obuf = my_out + (chunk_idx & 1) * kEpiSlab + row_off;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t* v = (u < 4) ? (v0 + u * 8) : (v1 + (u - 4) * 8);
+                    const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    uint32_t o[4];
+                    if (relu) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2_relu(f[2 * q], f[2 * q + 1]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    if (live) {
+                        if (warp == 3) tma_store_2d(&omap16, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                        else tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                    }
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp == 4) {
+        // ============================== W producer: this CTA's half of every tap ==============================
+        uint32_t it = 0;
+        for (int tile = pair; tile < a.num_tiles; tile += npairs) {
+            for (int cb = 0; cb < a.cin_blocks; ++cb) {
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int slot = it % a.w_stages;
+                    mbar_wait(&w_empty[slot], ((it / a.w_stages) & 1) ^ 1);
+                    const uint32_t leader_full = mapa_shared(smem_u32(&w_full[slot]), 0);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx_cluster(leader_full, 2 * kWHalf);
+                        else mbar_arrive_cluster(leader_full);
+                        tma_load_2d_2cta(&wmap_half, leader_full, sW + slot * kWHalf, (tap * a.cin_blocks + cb) * kTileK,
+                                         cta_n0 + (int)rank * (BN / 2));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ============================== MMA issuer (leader) ==============================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+            const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
+            const uint32_t sW_lo = umma_desc_lo(smem_u32(sW));
+            uint32_t ita = 0, itw = 0;
+            int tile_iter = 0;
+            for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
+                const int acc = tile_iter & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int cb = 0; cb < a.cin_blocks; ++cb, ++ita) {
+                    const int aslot = ita % kAStages;
+                    mbar_wait(&a_full[aslot], (ita / kAStages) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * kStripStage) >> 4);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++itw) {
+                        const int wslot = itw % a.w_stages;
+                        mbar_wait(&w_full[wslot], (itw / a.w_stages) & 1);
+                        tc_fence_after_sync();
+                        const uint64_t adesc =
+                            umma_desc_from_lo(a_lo + (uint32_t)((tap / 3) * (16384 >> 4) + (tap % 3) * (1024 >> 4)));
+                        const uint64_t bdesc = umma_desc_from_lo(sW_lo + ((uint32_t)(wslot * kWHalf) >> 4));
+                        const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
+                        if (elect_one()) {
+                            umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, first);
+#pragma unroll
+                            for (int k = 1; k < kTileK / 16; ++k)
+                                umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                            umma_commit_2cta(&w_empty[wslot]);
+                            if (tap == 8) {
+                                umma_commit_2cta(&a_empty[aslot]);
+                                if (cb == a.cin_blocks - 1) umma_commit_2cta(&tmem_full_bar[acc]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        // ============================== A producers: warp 6 + r loads input row h-1+r ==============================
+        const int prow = warp - 6;
+        uint32_t it = 0;
+        for (int tile = pair; tile < a.num_tiles; tile += npairs) {
+            const int strip = strip_of(tile);
+            const int ws = strip % a.tiles_w;
+            const int q = strip / a.tiles_w;
+            const int h = q % a.Hout;
+            const int n = q / a.Hout;  // past-the-end strips have n >= clips: the whole box is out of bounds -> zeros
+            for (int cb = 0; cb < a.cin_blocks; ++cb, ++it) {
+                const int slot = it % kAStages;
+                mbar_wait(&a_empty[slot], ((it / kAStages) & 1) ^ 1);
+                const uint32_t leader_full = mapa_shared(smem_u32(&a_full[slot]), 0);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx_cluster(leader_full, 16384);
+                    tma_load_5d_2cta(&amap, leader_full, sA + slot * kStripStage + prow * 16384, cb * kTileK, 0,
+                                     ws * kStripPixels - 1, h - 1 + prow, n);
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 5) tmem_dealloc_2cta(tmem_base, 2 * BN);
 }
 
 }  // namespace wd

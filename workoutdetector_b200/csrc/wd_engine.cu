@@ -121,7 +121,7 @@ struct ConvLayer {
     CUtensorMap omap;  // output [rows, Cout], box {64, 32} (persistent kernel's TMA store)
     CUtensorMap rmap;  // residual, same geometry
     CUtensorMap omap16;  // output, box {64, 16}: last warp of a 112-row strip tile
-    CUtensorMap wmap128; // W [Cout, K], box {64, 128}: one CTA's half of a 256-channel tile (cta_group::2 kernel)
+    CUtensorMap wmap_half; // W [Cout, K], box {64, tile_n / 2}: one CTA's half of a W tile (cta_group::2 kernels)
     CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
 };
 
@@ -544,7 +544,7 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
     return fail(WD_ERR_INVALID, "no v4 conv kernel for tile_n=%d a_mode=%d residual=%d", c.tile_n, c.a_mode, (int)res);
 }
 
-int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 1;  // cta_group::2 kernel for compute-bound 1x1 layers
+int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 2;  // cta_group::2 kernels: 1 = 1x1 conv1 layers, 2 = + 3x3 strips
 
 // CTA-pair kernel (wd_conv_2cta.cuh): 1x1 stride-1, no residual, 256-wide Cout tiles, K >= 256.
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
@@ -584,12 +584,62 @@ int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    WD_CUDA(cudaLaunchKernelEx(&cfg, wd::conv_2cta_kernel, c.wmap128, c.amap, c.omap, p));
+    WD_CUDA(cudaLaunchKernelEx(&cfg, wd::conv_2cta_kernel, c.wmap_half, c.amap, c.omap, p));
+    return WD_OK;
+}
+
+// CTA-pair strip kernel: 3x3 stride 1, W streamed per tap, tile_n 128 or 256.
+template <int BN>
+int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_2cta_strip_kernel<BN>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Conv2CtaStripArgs p{};
+    p.bias = a.bias;
+    p.Hout = a.Hout;
+    p.Wout = a.Wout;
+    p.cin_blocks = a.cin_blocks;
+    p.relu = a.relu;
+    p.n_tiles = c.Cout / BN;
+    p.tiles_w = a.Wout / wd::kStripPixels;
+    p.num_strips = a.M / wd::kStripRows;
+    p.num_tiles = ((p.num_strips + 1) / 2) * p.n_tiles;
+    const int whalf = (BN / 2) * 128;
+    const int fixed = 2 * wd::kStripStage + 8 * wd::kEpiSlab + 2048 + 1024;
+    p.w_stages = std::min(8, (232448 - fixed) / whalf);
+    p.off_w = 2 * wd::kStripStage;
+    p.off_out = p.off_w + p.w_stages * whalf;
+    p.off_bar = p.off_out + 8 * wd::kEpiSlab;
+    const int total = p.off_bar + 2048 + 1024;
+    int pairs = std::min(p.num_tiles, sm_count / 2);
+    pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(288);
+    cfg.dynamicSmemBytes = total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap, c.omap, c.omap16, p));
     return WD_OK;
 }
 
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
     if (eligible_2cta(c, a)) return launch_2cta(c, a, sm_count, st);
+    if (g_2cta >= 2 && c.a_mode == wd::A_STRIP && a.residual == nullptr && a.cin_blocks * 9 * c.tile_n * 128 > 73728) {
+        if (c.tile_n == 256) return launch_2cta_strip<256>(c, a, sm_count, st);
+        if (c.tile_n == 128) return launch_2cta_strip<128>(c, a, sm_count, st);
+    }
     if (c.a_mode == wd::A_STRIP) a.num_tiles = (a.M / wd::kStripRows) * a.n_tiles;  // tiles are 14-pixel row segments
     if (c.a_mode == wd::A_TAP) a.num_tiles = ((a.M + wd::kStripRows - 1) / wd::kStripRows) * a.n_tiles;
     switch (c.tile_n) {
@@ -732,9 +782,9 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     }
     const uint32_t box[2] = {64, (uint32_t)c.tile_n};
     WD_TRY(make_tmap_bf16(&c.wmap, c.w_packed, 2, dims, strides, box));
-    if (c.Cout % 256 == 0) {
-        const uint32_t box128[2] = {64, 128};
-        WD_TRY(make_tmap_bf16(&c.wmap128, c.w_packed, 2, dims, strides, box128));
+    if (c.tile_n >= 128) {
+        const uint32_t box_half[2] = {64, (uint32_t)c.tile_n / 2};
+        WD_TRY(make_tmap_bf16(&c.wmap_half, c.w_packed, 2, dims, strides, box_half));
     }
     return WD_OK;
 }
