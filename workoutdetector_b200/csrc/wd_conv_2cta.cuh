@@ -115,11 +115,18 @@ struct Conv2CtaArgs {
     int num_tiles;      // ceil(M / 256) * n_tiles; the number of pairs is a multiple of n_tiles
     uint32_t* trace;    // debug timeline (CTA 0), see Tracer
     int prefetch;       // L2-prefetch distance of the A operand in k-blocks (0 = off)
+    // TAP variant (A_TAP boxes, 112-row tiles; see wd_conv_v4.cuh): geometry of the convolution
+    int Hout, Wout, S, stride, pad, cin_blocks, tiles_w, tap_bh, num_m;  // num_m = ceil(M / 112)
 };
 
+// TAP = false: 1x1 stride-1 (one 3-D A box of 128 rows per k-block, TemporalShift = box t coordinate).
+// TAP = true : A_TAP geometry (3x3 / 1x1, stride 1 or 2): the CTA's tile is 14 output pixels (112 rows), every
+//              (tap, channel block) k-block is one or two strided 5-D boxes; a pair computes two consecutive tiles.
+template <bool TAP>
 __global__ void __launch_bounds__(384, 1)
 conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_constant__ CUtensorMap amap,
-                 const __grid_constant__ CUtensorMap omap, const Conv2CtaArgs a) {
+                 const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
+                 const Conv2CtaArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sOut = smem + k2cOffOut;
@@ -183,7 +190,9 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         uint32_t chunk_idx = 0;
         int tile_iter = 0;
         for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
-            const int mrow = (tile / a.n_tiles) * 256 + (int)rank * 128 + quarter * 32;
+            const int m_tile = (tile / a.n_tiles) * 2 + (int)rank;   // this CTA's 128-row (TAP: 112-row) tile
+            const bool live = !TAP || m_tile < a.num_m;
+            const int mrow = m_tile * (TAP ? kStripRows : kTileM) + quarter * 32;
             const int acc = tile_iter & 1;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
             const uint32_t leader_empty = mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0);
@@ -229,7 +238,12 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
-                    tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                    if (live) {
+                        if (TAP && quarter == 3)  // 112-row tiles: the last warp stores 16 rows only
+                            tma_store_2d(&omap16, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                        else
+                            tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                    }
                     tma_store_commit();
                 }
                 __syncwarp();
@@ -245,7 +259,22 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         uint32_t it = 0;
         Tracer tr{(a.trace && blockIdx.x == 0) ? a.trace + (is_w ? 1 : 2) * 2048 : nullptr, 0};
         for (int tile = pair; tile < a.num_tiles; tile += npairs) {
-            const int px0 = ((tile / a.n_tiles) * 256 + (int)rank * 128) >> 3;
+            const int m_tile = (tile / a.n_tiles) * 2 + (int)rank;
+            const int px0 = (m_tile * kTileM) >> 3;
+            // TAP: the tile is bh image rows of 14 / bh pixels; row j = (clip tn[j], output row toh[j], first pixel tow)
+            int tn[2] = {0, 0}, toh[2] = {0, 0}, tow = 0;
+            if (TAP) {
+                for (int j = 0; j < a.tap_bh; ++j) {
+                    int q = m_tile * a.tap_bh + j;
+                    if (a.tap_bh == 1) {
+                        tow = (q % a.tiles_w) * kStripPixels;
+                        q /= a.tiles_w;
+                    }
+                    toh[j] = q % a.Hout;
+                    tn[j] = q / a.Hout;   // past-the-end tiles: clip index out of bounds -> TMA fills zeros
+                }
+            }
+            int tap_r = 0, tap_s = 0, cb = 0;
             for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
                 const int slot = it % k2cStages;
                 tr.mark();
@@ -255,31 +284,30 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 uint8_t* stage = smem + slot * k2cStage;
                 if (elect_one()) {
                     // the leader announces the bytes of both CTAs for its operand, the peer just arrives
-                    if (rank == 0) mbar_arrive_expect_tx_cluster(leader_full, 2 * 16384);
+                    if (rank == 0) mbar_arrive_expect_tx_cluster(leader_full, 2 * ((TAP && !is_w) ? kStripRows * 128 : 16384));
                     else mbar_arrive_cluster(leader_full);
                     if (is_w) {
                         tma_load_2d_2cta(&wmap128, leader_full, stage + kATileBytes, kb * kTileK, cta_n0 + (int)rank * 128);
+                    } else if (TAP) {
+                        const int rows_per_box = kStripRows / a.tap_bh;
+                        for (int j = 0; j < a.tap_bh; ++j)
+                            tma_load_5d_2cta(&amap, leader_full, stage + j * rows_per_box * 128, cb * kTileK, 0,
+                                             tow * a.stride + tap_s - a.pad, toh[j] * a.stride + tap_r - a.pad, tn[j]);
                     } else {
                         const int c = kb * kTileK;
                         int dt = 0;
                         if (a.fold) dt = (c < a.fold) ? 1 : ((c < 2 * a.fold) ? -1 : 0);
                         tma_load_3d_2cta(&amap, leader_full, stage, c, dt, px0);
-                        // Optional L2 prefetch of the A box `prefetch` k-blocks ahead.  Measured: no gain — with A
-                        // forced L2-resident this kernel runs at 1336 TFLOP/s, with A from HBM at 1040: the layer
-                        // sits on the HBM roofline (205 MB in + 51 MB out in 50 us), not on HBM latency.
-                        if (a.prefetch > 0) {
-                            const int kq = kb + a.prefetch;
-                            const int t2 = tile + (kq / a.kblocks) * npairs;
-                            if (t2 < a.num_tiles) {
-                                const int c2 = (kq % a.kblocks) * kTileK;
-                                int dt2 = 0;
-                                if (a.fold) dt2 = (c2 < a.fold) ? 1 : ((c2 < 2 * a.fold) ? -1 : 0);
-                                tma_prefetch_l2_3d(&amap, c2, dt2, ((t2 / a.n_tiles) * 256 + (int)rank * 128) >> 3);
-                            }
-                        }
                     }
                 }
                 __syncwarp();
+                if (TAP && ++cb == a.cin_blocks) {  // k-blocks are tap-major: (r, s, channel block)
+                    cb = 0;
+                    if (++tap_s == a.S) {
+                        tap_s = 0;
+                        ++tap_r;
+                    }
+                }
             }
         }
     } else if (warp == 5 && rank == 0) {

@@ -544,18 +544,21 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
     return fail(WD_ERR_INVALID, "no v4 conv kernel for tile_n=%d a_mode=%d residual=%d", c.tile_n, c.a_mode, (int)res);
 }
 
-int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 2;  // cta_group::2 kernels: 1 = 1x1 conv1 layers, 2 = + 3x3 strips
+int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 3;  // cta_group::2 kernels: 1 = 1x1 conv1 layers, 2 = + 3x3 strips, 3 = + tap mode
 
 // CTA-pair kernel (wd_conv_2cta.cuh): 1x1 stride-1, no residual, 256-wide Cout tiles, K >= 256.
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
-    return g_2cta && c.a_mode == wd::A_TMA && c.tile_n == 256 && a.residual == nullptr && a.kblocks >= 4 &&
-           (a.fold == 0 || a.fold % 64 == 0) && c.Cout % 256 == 0;
+    if (!g_2cta || c.tile_n != 256 || a.residual != nullptr || c.Cout % 256 != 0) return false;
+    if (c.a_mode == wd::A_TMA) return a.kblocks >= 4 && (a.fold == 0 || a.fold % 64 == 0);
+    return g_2cta >= 3 && c.a_mode == wd::A_TAP && a.kblocks >= 8;   // stride-2 / 7x7 convolutions of layers 3-4
 }
 
-int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+template <bool TAP>
+int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
+    auto kfn = wd::conv_2cta_kernel<TAP>;
     if (!configured) {
-        WD_CUDA(cudaFuncSetAttribute(wd::conv_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::k2cSmem));
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::k2cSmem));
         configured = true;
     }
     wd::Conv2CtaArgs p{};
@@ -565,9 +568,14 @@ int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.fold = a.fold;
     p.relu = a.relu;
     p.n_tiles = c.Cout / 256;
-    p.num_tiles = ((a.M + 255) / 256) * p.n_tiles;
+    const int tile_rows = TAP ? wd::kStripRows : wd::kTileM;
+    p.num_m = (a.M + tile_rows - 1) / tile_rows;
+    p.num_tiles = ((p.num_m + 1) / 2) * p.n_tiles;
     p.trace = g_trace;
-    p.prefetch = g_prefetch_kblocks >= 0 ? g_prefetch_kblocks : 0;
+    p.prefetch = 0;
+    p.Hout = a.Hout; p.Wout = a.Wout; p.S = a.S; p.stride = a.stride; p.pad = a.pad; p.cin_blocks = a.cin_blocks;
+    p.tiles_w = std::max(1, a.Wout / wd::kStripPixels);
+    p.tap_bh = (TAP && a.Wout == 7) ? 2 : 1;
     int pairs = std::min(p.num_tiles, sm_count / 2);
     pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);  // a pair keeps one n-tile (bias)
     cudaLaunchConfig_t cfg{};
@@ -584,8 +592,12 @@ int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    WD_CUDA(cudaLaunchKernelEx(&cfg, wd::conv_2cta_kernel, c.wmap_half, c.amap, c.omap, p));
+    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap, c.omap, c.omap16, p));
     return WD_OK;
+}
+
+int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    return c.a_mode == wd::A_TAP ? launch_2cta_t<true>(c, a, sm_count, st) : launch_2cta_t<false>(c, a, sm_count, st);
 }
 
 // CTA-pair strip kernel: 3x3 stride 1, W streamed per tap, tile_n 128 or 256.
@@ -766,9 +778,10 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     else if (use_strip && c.k == 3 && c.stride == 1 && c.Wout % wd::kStripPixels == 0 && c.Wout >= wd::kStripPixels)
         c.a_mode = wd::A_STRIP;
     else if (use_strip && v4 && g_tap && c.fold == 0 && (c.k == 3 || c.stride == 2) &&
-             (c.Wout % wd::kStripPixels == 0 || (c.Wout == 7 && g_tap >= 2)))
+             (c.Wout % wd::kStripPixels == 0 || (c.Wout == 7 && (g_tap >= 2 || (g_2cta >= 3 && c.tile_n == 256)))))
         c.a_mode = wd::A_TAP;  // stride-2 convolutions: one TMA box per (tap, channel block).  7-pixel rows (two boxes per
-                               // tile, 12.5 % dead rows) measured slower than the cp.async gather: opt-in (WD_TAP=2)
+                               // tile, 12.5 % dead rows) are slower than the cp.async gather on one CTA (WD_TAP=2 forces
+                               // them) but faster on a CTA pair, which is where they run by default
     else
         c.a_mode = wd::A_GATHER;
     WD_CUDA(cudaMalloc(&c.w_packed, p.size() * 2));
@@ -1096,7 +1109,8 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
     } else if (!strcmp(key, "use_2cta")) {
-        g_2cta = value ? 1 : 0;
+        if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "use_2cta must be 0..3");
+        g_2cta = value;
     } else if (!strcmp(key, "pdl")) {
         g_pdl = value ? 1 : 0;
     } else if (!strcmp(key, "prefetch_kblocks")) {
