@@ -240,11 +240,11 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_step")
-    # "launch" here = the 53 tcgen05 launches of one step taken together (52 x conv_v4_kernel + stem_pool_kernel):
+    # "launch" here = the 53 tcgen05 launches of one step taken together (52 convolutions + stem_pool_kernel):
     # achieved = their algorithmic FLOPs / the sum of their CUDA-event durations; traffic = their summed DRAM bytes.
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["sustained"], traffic=traffic,
-                    kernel="conv_v4_kernel (52 launches) + stem_pool_kernel (1) per step, aggregated",
+                    kernel="the 53 tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), stem_pool_kernel",
                     frac_of_burst=achieved / peaks["burst"], peak_source=peaks["source"],
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / max(sum(op_ms), 1e-9),
                     dram_gbs=(traffic / (conv_ms * 1e-3) / 1e9) if traffic else None,

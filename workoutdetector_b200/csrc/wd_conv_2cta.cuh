@@ -100,10 +100,17 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 }
 
 constexpr int k2cStage = kATileBytes + 128 * kTileK * 2;  // A 16 KiB + half of the 256-row W tile 16 KiB
-constexpr int k2cStages = 5;
-constexpr int k2cOffOut = k2cStages * k2cStage;            // 8 warps x 2 x 4 KiB output slabs
-constexpr int k2cOffBar = k2cOffOut + 16 * kEpiSlab;
-constexpr int k2cSmem = k2cOffBar + 2048 + 1024;
+// Shared-memory plan: RES keeps three in-place residual/output slabs per epilogue warp (8 x 3 x 4 KiB) and four
+// stages; without a residual there are two output slabs per warp and five stages.  Both fill the 227 KiB exactly.
+template <bool RES>
+struct Plan2Cta {
+    static constexpr int kStages = RES ? 4 : 5;
+    static constexpr int kSlabsPerWarp = RES ? 3 : 2;
+    static constexpr int kOffOut = kStages * k2cStage;
+    static constexpr int kOffBar = kOffOut + 8 * kSlabsPerWarp * kEpiSlab;
+    static constexpr int kSmem = kOffBar + 2048 + 1024;
+    static_assert(kSmem <= 232448, "over the 227 KiB opt-in limit");
+};
 
 struct Conv2CtaArgs {
     const float* bias;  // [Cout]
@@ -122,11 +129,16 @@ struct Conv2CtaArgs {
 // TAP = false: 1x1 stride-1 (one 3-D A box of 128 rows per k-block, TemporalShift = box t coordinate).
 // TAP = true : A_TAP geometry (3x3 / 1x1, stride 1 or 2): the CTA's tile is 14 output pixels (112 rows), every
 //              (tap, channel block) k-block is one or two strided 5-D boxes; a pair computes two consecutive tiles.
-template <bool TAP>
+// RES: residual added in place in the slab the TMA load delivered it to (as the 8-warp epilogue of conv_v4_kernel).
+template <bool TAP, bool RES>
 __global__ void __launch_bounds__(384, 1)
 conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_constant__ CUtensorMap amap,
                  const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
-                 const Conv2CtaArgs a) {
+                 const __grid_constant__ CUtensorMap rmap, const Conv2CtaArgs a) {
+    using P = Plan2Cta<RES>;
+    constexpr int k2cStages = P::kStages;
+    constexpr int k2cOffOut = P::kOffOut;
+    constexpr int k2cOffBar = P::kOffBar;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sOut = smem + k2cOffOut;
@@ -160,6 +172,10 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 mbar_init(&tmem_full_bar[s], 1);
                 mbar_init(&tmem_empty_bar[s], 16);
             }
+            if (RES) {
+                tma_prefetch_desc(&rmap);
+                for (int s = 0; s < 24; ++s) mbar_init(&bars[192 + s], 1);
+            }
             fence_barrier_init();
         }
         __syncwarp();
@@ -183,10 +199,29 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         // about as long as a four-warp epilogue; two warps per scheduler overlap each other's issue latencies)
         // ==========================================================================================
         const int quarter = warp & 3, half = warp >> 3;
-        uint8_t* my_out = sOut + (half * 4 + quarter) * 2 * kEpiSlab;
+        const int eidx = half * 4 + quarter;
+        uint8_t* my_out = sOut + eidx * P::kSlabsPerWarp * kEpiSlab;
+        uint64_t* my_bar = bars + 192 + eidx * 3;  // RES: one barrier per residual slab
         const uint32_t row_off = lane * 128;
         const uint32_t sw = lane & 7;
         const bool relu = a.relu != 0;
+        const int my_tiles = (a.num_tiles - pair + npairs - 1) / npairs;
+        const uint32_t total = (uint32_t)my_tiles * 2;  // chunks of this warp: two per tile
+        auto issue_res = [&](uint32_t q) {  // residual chunk q of this warp -> slab q % 3
+            const int t2 = pair + (int)(q >> 1) * npairs;
+            const int m2 = (t2 / a.n_tiles) * 2 + (int)rank;
+            const uint32_t slot = q % 3;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&my_bar[slot], kEpiSlab);
+                tma_load_2d(&rmap, &my_bar[slot], my_out + slot * kEpiSlab, cta_n0 + (2 * half + (int)(q & 1)) * 64,
+                            m2 * kTileM + quarter * 32);
+            }
+            __syncwarp();
+        };
+        if (RES) {
+            if (total > 0) issue_res(0);
+            if (total > 1) issue_res(1);
+        }
         uint32_t chunk_idx = 0;
         int tile_iter = 0;
         for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
@@ -200,53 +235,73 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
             tc_fence_after_sync();
 #pragma unroll 1
             for (int c = 2 * half; c < 2 * half + 2; ++c, ++chunk_idx) {
-                float4 bb[16];
-                const float4* bsrc = reinterpret_cast<const float4*>(sBias + c * 64);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
-                uint32_t v0[32], v1[32];
-                tmem_ld32(taddr + c * 64, v0);
-                tmem_ld32(taddr + c * 64 + 32, v1);
-                tmem_ld_wait();
-                if (c == 2 * half + 1) {  // this warp's share is drained: tell the leader's MMA issuer
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (elect_one()) mbar_arrive_cluster(leader_empty);
+                const uint32_t slot = RES ? chunk_idx % 3 : (chunk_idx & 1);
+                uint8_t* obuf = my_out + slot * kEpiSlab + row_off;
+                if (RES) mbar_wait(&my_bar[slot], (chunk_idx / 3) & 1);  // residual chunk has landed in its slab
+                else {
+                    if (elect_one()) tma_store_wait_read1();  // the store that last read this slab is done reading
                     __syncwarp();
                 }
-                if (elect_one()) tma_store_wait_read1();
-                __syncwarp();
-                uint8_t* obuf = my_out + (chunk_idx & 1) * kEpiSlab + row_off;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t* v = (u < 4) ? (v0 + u * 8) : (v1 + (u - 4) * 8);
-                    const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
-                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
-                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
-                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
-                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
-                    uint32_t o[4];
-                    if (relu) {
+                for (int hf = 0; hf < 2; ++hf) {  // two 32-column halves keep the live registers low
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 64 + hf * 32, v);
+                    uint4 rr[4];
+                    if (RES) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2_relu(f[2 * q], f[2 * q + 1]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                        for (int u = 0; u < 4; ++u) rr[u] = *reinterpret_cast<const uint4*>(obuf + (((hf * 4 + u) ^ sw) << 4));
                     }
-                    *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    float4 bb[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) bb[u] = reinterpret_cast<const float4*>(sBias + c * 64 + hf * 32)[u];
+                    tmem_ld_wait();
+                    if (hf == 1 && c == 2 * half + 1) {  // this warp's share is drained: tell the leader's MMA issuer
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (elect_one()) mbar_arrive_cluster(leader_empty);
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                        float f[8] = {__uint_as_float(v[u * 8 + 0]) + b0.x, __uint_as_float(v[u * 8 + 1]) + b0.y,
+                                      __uint_as_float(v[u * 8 + 2]) + b0.z, __uint_as_float(v[u * 8 + 3]) + b0.w,
+                                      __uint_as_float(v[u * 8 + 4]) + b1.x, __uint_as_float(v[u * 8 + 5]) + b1.y,
+                                      __uint_as_float(v[u * 8 + 6]) + b1.z, __uint_as_float(v[u * 8 + 7]) + b1.w};
+                        if (RES) {
+                            const uint32_t rw[4] = {rr[u].x, rr[u].y, rr[u].z, rr[u].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                f[2 * q] += __uint_as_float(rw[q] << 16);
+                                f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                            }
+                        }
+                        uint32_t o[4];
+                        if (relu) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2_relu(f[2 * q], f[2 * q + 1]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(obuf + (((hf * 4 + u) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
                     if (live) {
                         if (TAP && quarter == 3)  // 112-row tiles: the last warp stores 16 rows only
-                            tma_store_2d(&omap16, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                            tma_store_2d(&omap16, my_out + slot * kEpiSlab, cta_n0 + c * 64, mrow);
                         else
-                            tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                            tma_store_2d(&omap, my_out + slot * kEpiSlab, cta_n0 + c * 64, mrow);
                     }
                     tma_store_commit();
+                    // RES: slab (j+2) % 3 == (j-1) % 3 is free once the store of chunk j-1 has read it
+                    if (RES && chunk_idx + 2 < total) tma_store_wait_read1();
                 }
                 __syncwarp();
+                if (RES && chunk_idx + 2 < total) issue_res(chunk_idx + 2);
             }
         }
         if (elect_one()) tma_store_wait_all();

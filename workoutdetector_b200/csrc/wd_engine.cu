@@ -544,21 +544,24 @@ int launch_v4_bn(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaSt
     return fail(WD_ERR_INVALID, "no v4 conv kernel for tile_n=%d a_mode=%d residual=%d", c.tile_n, c.a_mode, (int)res);
 }
 
-int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 3;  // cta_group::2 kernels: 1 = 1x1 conv1 layers, 2 = + 3x3 strips, 3 = + tap mode
+int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 4;  // cta_group::2 kernels: 1 = 1x1 conv1, 2 = + 3x3 strips, 3 = + tap mode, 4 = + residual conv3
 
 // CTA-pair kernel (wd_conv_2cta.cuh): 1x1 stride-1, no residual, 256-wide Cout tiles, K >= 256.
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
-    if (!g_2cta || c.tile_n != 256 || a.residual != nullptr || c.Cout % 256 != 0) return false;
+    if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0) return false;
+    if (a.residual != nullptr)  // conv3 of layers 3-4 (K >= 256): pair kernel with the in-place residual epilogue
+        return g_2cta >= 4 && c.a_mode == wd::A_TMA && a.kblocks >= 4 && a.fold == 0;
     if (c.a_mode == wd::A_TMA) return a.kblocks >= 4 && (a.fold == 0 || a.fold % 64 == 0);
     return g_2cta >= 3 && c.a_mode == wd::A_TAP && a.kblocks >= 8;   // stride-2 / 7x7 convolutions of layers 3-4
 }
 
-template <bool TAP>
+template <bool TAP, bool RES>
 int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = wd::conv_2cta_kernel<TAP>;
+    auto kfn = wd::conv_2cta_kernel<TAP, RES>;
+    constexpr int smem = wd::Plan2Cta<RES>::kSmem;
     if (!configured) {
-        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::k2cSmem));
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     wd::Conv2CtaArgs p{};
@@ -581,7 +584,7 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(384);
-    cfg.dynamicSmemBytes = wd::k2cSmem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -592,12 +595,14 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap, c.omap, c.omap16, p));
+    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap, c.omap, c.omap16, c.rmap, p));
     return WD_OK;
 }
 
 int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
-    return c.a_mode == wd::A_TAP ? launch_2cta_t<true>(c, a, sm_count, st) : launch_2cta_t<false>(c, a, sm_count, st);
+    if (a.residual != nullptr) return launch_2cta_t<false, true>(c, a, sm_count, st);
+    return c.a_mode == wd::A_TAP ? launch_2cta_t<true, false>(c, a, sm_count, st)
+                                 : launch_2cta_t<false, false>(c, a, sm_count, st);
 }
 
 // CTA-pair strip kernel: 3x3 stride 1, W streamed per tap, tile_n 128 or 256.
@@ -1109,7 +1114,7 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
     } else if (!strcmp(key, "use_2cta")) {
-        if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "use_2cta must be 0..3");
+        if (value < 0 || value > 4) return fail(WD_ERR_INVALID, "use_2cta must be 0..4");
         g_2cta = value;
     } else if (!strcmp(key, "pdl")) {
         g_pdl = value ? 1 : 0;
