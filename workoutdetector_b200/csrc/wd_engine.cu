@@ -1294,7 +1294,12 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int 
     if (n_clips == 0) return WD_OK;
     if (!host || !host_logits) return fail(WD_ERR_INVALID, "host_frames/host_logits must not be NULL");
     WD_CUDA(cudaSetDevice(e->desc.device));
-    const int chunk = std::min(e->desc.max_clips, 16);
+    // Chunk schedule: a small first chunk (its H2D copy is the only one nothing can hide) and then chunks as large
+    // as the staging buffers allow, so that the convolutions run at large-batch efficiency while the next copy
+    // streams over PCIe.  WD_HOST_CHUNK overrides the size of the later chunks.
+    static const int env_chunk = getenv("WD_HOST_CHUNK") ? atoi(getenv("WD_HOST_CHUNK")) : 0;
+    const int chunk = std::max(1, std::min(e->desc.max_clips, env_chunk > 0 ? env_chunk : 64));
+    const int first_chunk = std::min(chunk, 8);
     const size_t clip_bytes = (size_t)8 * H * W * 3;
     const int C = e->desc.num_class;
     if (!e->hstream[0]) {
@@ -1322,7 +1327,7 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int 
     cudaStream_t cp = e->hstream[1];
     int done = 0, idx = 0;
     while (done < n_clips) {
-        const int nc = std::min(chunk, n_clips - done);
+        const int nc = std::min(idx == 0 ? first_chunk : chunk, n_clips - done);
         const int slot = idx & 1;
         // wait until the compute that last used this slot has finished before overwriting its staging buffer
         if (idx >= 2) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
