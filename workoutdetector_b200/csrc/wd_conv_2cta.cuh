@@ -99,14 +99,16 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
                  : "memory");
 }
 
-constexpr int k2cStage = kATileBytes + 128 * kTileK * 2;  // A 16 KiB + half of the 256-row W tile 16 KiB
-// Shared-memory plan: RES keeps three in-place residual/output slabs per epilogue warp (8 x 3 x 4 KiB) and four
-// stages; without a residual there are two output slabs per warp and five stages.  Both fill the 227 KiB exactly.
-template <bool RES>
+// Shared-memory plan: a stage is this CTA's A tile (16 KiB) + its half of the W tile (BN/2 rows).  RES keeps three
+// in-place residual/output slabs per epilogue warp (8 x 3 x 4 KiB), otherwise two output slabs per warp; the stages
+// take what is left of the 227 KiB (BN 256: 4 / 5 stages, BN 128: 5 / 6).
+template <int BN, bool RES>
 struct Plan2Cta {
-    static constexpr int kStages = RES ? 4 : 5;
+    static constexpr int kStage = kATileBytes + (BN / 2) * kTileK * 2;
     static constexpr int kSlabsPerWarp = RES ? 3 : 2;
-    static constexpr int kOffOut = kStages * k2cStage;
+    static constexpr int kStages = (232448 - 3072 - 8 * kSlabsPerWarp * kEpiSlab) / kStage > 6
+                                       ? 6 : (232448 - 3072 - 8 * kSlabsPerWarp * kEpiSlab) / kStage;
+    static constexpr int kOffOut = kStages * kStage;
     static constexpr int kOffBar = kOffOut + 8 * kSlabsPerWarp * kEpiSlab;
     static constexpr int kSmem = kOffBar + 2048 + 1024;
     static_assert(kSmem <= 232448, "over the 227 KiB opt-in limit");
@@ -118,7 +120,7 @@ struct Conv2CtaArgs {
     int kblocks;        // Cin / 64
     int fold;           // TemporalShift fold (multiple of 64) or 0
     int relu;
-    int n_tiles;        // Cout / 256
+    int n_tiles;        // Cout / BN
     int num_tiles;      // ceil(M / 256) * n_tiles; the number of pairs is a multiple of n_tiles
     uint32_t* trace;    // debug timeline (CTA 0), see Tracer
     int prefetch;       // L2-prefetch distance of the A operand in k-blocks (0 = off)
@@ -130,13 +132,15 @@ struct Conv2CtaArgs {
 // TAP = true : A_TAP geometry (3x3 / 1x1, stride 1 or 2): the CTA's tile is 14 output pixels (112 rows), every
 //              (tap, channel block) k-block is one or two strided 5-D boxes; a pair computes two consecutive tiles.
 // RES: residual added in place in the slab the TMA load delivered it to (as the 8-warp epilogue of conv_v4_kernel).
-template <bool TAP, bool RES>
+template <int BN, bool TAP, bool RES>
 __global__ void __launch_bounds__(384, 1)
 conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_constant__ CUtensorMap amap,
                  const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
                  const __grid_constant__ CUtensorMap rmap, const Conv2CtaArgs a) {
-    using P = Plan2Cta<RES>;
+    using P = Plan2Cta<BN, RES>;
+    constexpr int k2cStage = P::kStage;
     constexpr int k2cStages = P::kStages;
+    constexpr int kCpw = BN / 128;  // 64-column chunks per epilogue warp
     constexpr int k2cOffOut = P::kOffOut;
     constexpr int k2cOffBar = P::kOffBar;
     extern __shared__ uint8_t smem_raw[];
@@ -157,7 +161,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
     const uint32_t rank = cluster_ctarank();
     const int pair = (int)blockIdx.x >> 1;
     const int npairs = (int)gridDim.x >> 1;
-    const int cta_n0 = (pair % a.n_tiles) * 256;
+    const int cta_n0 = (pair % a.n_tiles) * BN;
 
     if (warp == 4) {
         if (elect_one()) {
@@ -181,11 +185,11 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         __syncwarp();
     }
     if (warp == 5) {
-        tmem_alloc_2cta(tmem_ptr, 512);
+        tmem_alloc_2cta(tmem_ptr, 2 * BN);
         tmem_relinquish_2cta();
     }
     if (warp < 4)
-        for (int i = tid; i < 256; i += 128) sBias[i] = a.bias[cta_n0 + i];  // warps 0-3 = threads 0..127
+        for (int i = tid; i < BN; i += 128) sBias[i] = a.bias[cta_n0 + i];  // warps 0-3 = threads 0..127
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
@@ -206,14 +210,14 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         const uint32_t sw = lane & 7;
         const bool relu = a.relu != 0;
         const int my_tiles = (a.num_tiles - pair + npairs - 1) / npairs;
-        const uint32_t total = (uint32_t)my_tiles * 2;  // chunks of this warp: two per tile
+        const uint32_t total = (uint32_t)my_tiles * kCpw;  // chunks of this warp
         auto issue_res = [&](uint32_t q) {  // residual chunk q of this warp -> slab q % 3
-            const int t2 = pair + (int)(q >> 1) * npairs;
+            const int t2 = pair + (int)(q / kCpw) * npairs;
             const int m2 = (t2 / a.n_tiles) * 2 + (int)rank;
             const uint32_t slot = q % 3;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&my_bar[slot], kEpiSlab);
-                tma_load_2d(&rmap, &my_bar[slot], my_out + slot * kEpiSlab, cta_n0 + (2 * half + (int)(q & 1)) * 64,
+                tma_load_2d(&rmap, &my_bar[slot], my_out + slot * kEpiSlab, cta_n0 + (kCpw * half + (int)(q % kCpw)) * 64,
                             m2 * kTileM + quarter * 32);
             }
             __syncwarp();
@@ -229,12 +233,12 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
             const bool live = !TAP || m_tile < a.num_m;
             const int mrow = m_tile * (TAP ? kStripRows : kTileM) + quarter * 32;
             const int acc = tile_iter & 1;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
             const uint32_t leader_empty = mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0);
             mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
             tc_fence_after_sync();
 #pragma unroll 1
-            for (int c = 2 * half; c < 2 * half + 2; ++c, ++chunk_idx) {
+            for (int c = kCpw * half; c < kCpw * half + kCpw; ++c, ++chunk_idx) {
                 const uint32_t slot = RES ? chunk_idx % 3 : (chunk_idx & 1);
                 uint8_t* obuf = my_out + slot * kEpiSlab + row_off;
                 if (RES) mbar_wait(&my_bar[slot], (chunk_idx / 3) & 1);  // residual chunk has landed in its slab
@@ -255,7 +259,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
 #pragma unroll
                     for (int u = 0; u < 8; ++u) bb[u] = reinterpret_cast<const float4*>(sBias + c * 64 + hf * 32)[u];
                     tmem_ld_wait();
-                    if (hf == 1 && c == 2 * half + 1) {  // this warp's share is drained: tell the leader's MMA issuer
+                    if (hf == 1 && c == kCpw * half + kCpw - 1) {  // this warp's share is drained: tell the leader's MMA issuer
                         tc_fence_before_sync();
                         __syncwarp();
                         if (elect_one()) mbar_arrive_cluster(leader_empty);
@@ -339,10 +343,11 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 uint8_t* stage = smem + slot * k2cStage;
                 if (elect_one()) {
                     // the leader announces the bytes of both CTAs for its operand, the peer just arrives
-                    if (rank == 0) mbar_arrive_expect_tx_cluster(leader_full, 2 * ((TAP && !is_w) ? kStripRows * 128 : 16384));
+                    if (rank == 0)
+                        mbar_arrive_expect_tx_cluster(leader_full, is_w ? BN * kTileK * 2 : 2 * (TAP ? kStripRows * 128 : 16384));
                     else mbar_arrive_cluster(leader_full);
                     if (is_w) {
-                        tma_load_2d_2cta(&wmap128, leader_full, stage + kATileBytes, kb * kTileK, cta_n0 + (int)rank * 128);
+                        tma_load_2d_2cta(&wmap128, leader_full, stage + kATileBytes, kb * kTileK, cta_n0 + (int)rank * (BN / 2));
                     } else if (TAP) {
                         const int rows_per_box = kStripRows / a.tap_bh;
                         for (int j = 0; j < a.tap_bh; ++j)
@@ -369,7 +374,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         // ==========================================================================================
         // MMA issuer (leader CTA only): 256 x 256 x 16 per instruction
         // ==========================================================================================
-        constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+        constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
         const uint32_t s_lo = umma_desc_lo(smem_u32(smem));
         uint32_t it = 0;
         int tile_iter = 0;
@@ -379,7 +384,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
             tr.mark();
             mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + acc * 256;
+            const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
                 const int slot = it % k2cStages;
                 tr.mark();

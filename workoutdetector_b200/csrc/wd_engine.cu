@@ -548,6 +548,8 @@ int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 4;  // cta_group::2 k
 
 // CTA-pair kernel (wd_conv_2cta.cuh): 1x1 stride-1, no residual, 256-wide Cout tiles, K >= 256.
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
+    // 256-wide tiles only: the BN = 128 instantiation of conv_2cta_kernel faults on the device (not a barrier
+    // time-out; cause not found in round 1) and is not dispatched.
     if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0) return false;
     if (a.residual != nullptr)  // conv3 of layers 3-4 (K >= 256): pair kernel with the in-place residual epilogue
         return g_2cta >= 4 && c.a_mode == wd::A_TMA && a.kblocks >= 4 && a.fold == 0;
@@ -555,11 +557,11 @@ bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
     return g_2cta >= 3 && c.a_mode == wd::A_TAP && a.kblocks >= 8;   // stride-2 / 7x7 convolutions of layers 3-4
 }
 
-template <bool TAP, bool RES>
+template <int BN, bool TAP, bool RES>
 int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = wd::conv_2cta_kernel<TAP, RES>;
-    constexpr int smem = wd::Plan2Cta<RES>::kSmem;
+    auto kfn = wd::conv_2cta_kernel<BN, TAP, RES>;
+    constexpr int smem = wd::Plan2Cta<BN, RES>::kSmem;
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -570,7 +572,7 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     p.kblocks = a.kblocks;
     p.fold = a.fold;
     p.relu = a.relu;
-    p.n_tiles = c.Cout / 256;
+    p.n_tiles = c.Cout / BN;
     const int tile_rows = TAP ? wd::kStripRows : wd::kTileM;
     p.num_m = (a.M + tile_rows - 1) / tile_rows;
     p.num_tiles = ((p.num_m + 1) / 2) * p.n_tiles;
@@ -600,9 +602,9 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
 }
 
 int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
-    if (a.residual != nullptr) return launch_2cta_t<false, true>(c, a, sm_count, st);
-    return c.a_mode == wd::A_TAP ? launch_2cta_t<true, false>(c, a, sm_count, st)
-                                 : launch_2cta_t<false, false>(c, a, sm_count, st);
+    if (a.residual != nullptr) return launch_2cta_t<256, false, true>(c, a, sm_count, st);
+    return c.a_mode == wd::A_TAP ? launch_2cta_t<256, true, false>(c, a, sm_count, st)
+                                 : launch_2cta_t<256, false, false>(c, a, sm_count, st);
 }
 
 // CTA-pair strip kernel: 3x3 stride 1, W streamed per tap, tile_n 128 or 256.
@@ -1439,6 +1441,12 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
             wd::ConvArgs a = conv_args(c, x, y, residual, clips);
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+            if (getenv("WD_DEBUG_WAIT")) {
+                const int one = 1;
+                const uint32_t zero = 0;
+                cudaMemcpyToSymbol(wd::g_wd_wait_nofatal, &one, sizeof(int));
+                cudaMemcpyToSymbol(wd::g_wd_wait_dbg_n, &zero, sizeof(uint32_t));
+            }
             const char* trace_path = getenv("WD_TRACE");
             if (trace_path) {
                 cudaMalloc(&g_trace, 4 * 2048 * sizeof(uint32_t));
@@ -1455,6 +1463,15 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
                     fwrite(h.data(), 4, h.size(), f);
                     fclose(f);
                 }
+            }
+            if (getenv("WD_DEBUG_WAIT")) {
+                cudaDeviceSynchronize();
+                uint32_t n = 0, rec[4 * 64];
+                cudaMemcpyFromSymbol(&n, wd::g_wd_wait_dbg_n, sizeof(uint32_t));
+                cudaMemcpyFromSymbol(rec, wd::g_wd_wait_dbg, sizeof(rec));
+                for (uint32_t i = 0; i < n && i < 64; ++i)
+                    fprintf(stderr, "[wd wait timeout] block %u warp %u bar smem 0x%x parity %u\n", rec[4 * i],
+                            rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
             }
             if (rc == WD_OK && iters > 0 && ms_out) {
                 cudaEvent_t e0, e1;

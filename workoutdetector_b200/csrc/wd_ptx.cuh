@@ -79,11 +79,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef WD_BOUNDED_WAIT
 #define WD_BOUNDED_WAIT 1
 #endif
+// Debug aid (WD_DEBUG_WAIT=1 with the single-layer hooks): instead of trapping, a wait that does not complete records
+// {blockIdx, warp, barrier smem address, parity} and gives up, so the kernel ends and the host can print the record.
+__device__ uint32_t g_wd_wait_dbg[4 * 64];
+__device__ uint32_t g_wd_wait_dbg_n;
+__device__ int g_wd_wait_nofatal;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if WD_BOUNDED_WAIT
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (g_wd_wait_nofatal ? (1u << 20) : (1u << 26))) {
+            if (!g_wd_wait_nofatal) __trap();
+            if ((threadIdx.x & 31) == 0) {
+                const uint32_t i = atomicAdd(&g_wd_wait_dbg_n, 1u);
+                if (i < 64) {
+                    g_wd_wait_dbg[4 * i] = blockIdx.x;
+                    g_wd_wait_dbg[4 * i + 1] = threadIdx.x >> 5;
+                    g_wd_wait_dbg[4 * i + 2] = smem_u32(bar);
+                    g_wd_wait_dbg[4 * i + 3] = parity;
+                }
+            }
+            return;
+        }
     }
 #else
     while (!mbar_try_wait(bar, parity)) {
