@@ -125,7 +125,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             if (kTmaA) tma_prefetch_desc(&amap);
             if (HAS_RES) tma_prefetch_desc(&rmap);
             if (k112) tma_prefetch_desc(&omap16);
-            if (AMODE == A_TMA && a.fold == 32) tma_prefetch_desc(&amap32);
+            if (AMODE == A_TMA && (a.fold == 32 || p.kb_split > 0)) tma_prefetch_desc(&amap32);
             for (int s = 0; s < 8; ++s) {
                 mbar_init(&bars[s], merged ? 2 : (kStrip ? 3 : (kTmaA ? 1 : 128)));
                 mbar_init(&a_empty[s], 1);
@@ -527,7 +527,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 step_h = sq % a.Hout;
                 step_n = sq / a.Hout;
             }
-            const int ahead = (!k112 && p.prefetch_kblocks > 0) ? (p.prefetch_kblocks + a_steps - 1) / a_steps : 0;
+            const int ahead = (!k112 && p.kb_split == 0 && p.prefetch_kblocks > 0) ? (p.prefetch_kblocks + a_steps - 1) / a_steps : 0;
             const int m_tiles_total = num_tiles / a.n_tiles;
             uint32_t it = 0;
             Tracer tr{(p.trace && blockIdx.x == 0 && warp == 6) ? p.trace + 2 * 2048 : nullptr, 0};
@@ -565,6 +565,9 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                             for (int j = 0; j < p.tap_bh; ++j)
                                 tma_load_5d(&amap, &a_full[slot], dst + j * rows_per_box * 128, cb * kTileK, 0,
                                             tow * a.stride + tap_s - a.pad, toh[j] * a.stride + tap_r - a.pad, tn[j]);
+                        } else if (p.kb_split > 0 && as >= p.kb_split) {  // fused downsample: block-input channels
+                            mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
+                            tma_load_3d(&amap32, &a_full[slot], dst, (as - p.kb_split) * kTileK, 0, px0);
                         } else if (a.fold == 32 && as == 0) {
                             mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
                             tma_load_3d(&amap32, &a_full[slot], dst, 0, 1, px0);          // channels 0..31 from t+1

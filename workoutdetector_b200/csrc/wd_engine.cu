@@ -110,6 +110,10 @@ struct ConvLayer {
     int Hin = 0, Win = 0, Hout = 0, Wout = 0;
     int fold = 0, relu = 0;
     bool stem = false;
+    int fuse_ds = -1;       // conv3 of a stride-1 block 0: index of the downsample conv folded into its K dimension
+    bool fused_away = false; // downsample conv that runs inside the block's conv3 (kept for its weights)
+    int kb_split = 0;       // fused conv3: k-blocks [0, kb_split) come from the block's conv2 output, the rest from the
+                            // block input (second A map)
     // device data
     void* w_packed = nullptr;   // bf16 [Cout, Kp] (BF16 mode) or fp32 [K, Cout] (FP32 mode)
     float* bias = nullptr;      // [Cout]
@@ -131,6 +135,7 @@ struct Op {
     int in_buf = -1;         // -1 = external frames
     int out_buf = -1;
     int res_buf = -1;        // residual buffer or -1
+    int in2_buf = -1;        // fused downsample: the block input (second A source)
     std::string name;
     int C = 0, H = 0, W = 0;  // output dims per frame
     double macs_per_clip = 0;
@@ -145,6 +150,8 @@ struct wd_engine {
     int tile_n_max = 256;
     int persistent = 3;  // 0: one tile per CTA, 1: persistent v2, 2: v3 (W-resident, strip 3x3), 3: v4 (uniform MMA issue)
     int use_strip = 1;
+    int fuse_ds = 1;         // fold the stride-1 downsample (layer1.0) into conv3's K dimension (current plan)
+    int fuse_ds_requested = 1;  // WD_FUSE_DS at create time
     int stem_seg_rows = 28;  // pooled rows per work unit of the fused stem + max-pool kernel
     int sm_count = 148;
     std::vector<ConvLayer> convs;
@@ -264,15 +271,31 @@ int build_plan(wd_engine* e) {
             add_conv_op(c2, fr[0], fr[1], -1);
             const int Ho = e->convs[c2].Hout;
             int idbuf = cur;
+            // Block 0 of layer 1 (stride 1): out = relu(W3*y2 + b3 + Wd*x + bd) is ONE GEMM over the concatenated
+            // K = [y2 | x] with weights [W3 | Wd] and bias b3 + bd — the 1.6 MB/frame downsample output is never written
+            // or read back as a residual (bf16 mode; FP32_VALIDATE keeps the reference's op sequence).
+            const bool fuse = (b == 0 && stride == 1 && e->desc.mode == WD_MODE_BF16 && e->fuse_ds);
+            int cd = -1;
             if (b == 0) {
-                const int cd = add_conv(nm + ".downsample", pre + ".downsample.0.weight", "", pre + ".downsample.1",
-                                        inplanes, outp, 1, stride, H, 0, 0);
-                add_conv_op(cd, cur, fr[2], -1);
-                idbuf = fr[2];
+                cd = add_conv(nm + ".downsample", pre + ".downsample.0.weight", "", pre + ".downsample.1", inplanes, outp,
+                              1, stride, H, 0, 0);
+                if (fuse) {
+                    e->convs[cd].fused_away = true;
+                } else {
+                    add_conv_op(cd, cur, fr[2], -1);
+                    idbuf = fr[2];
+                }
             }
             const int c3 =
                 add_conv(nm + ".conv3", pre + ".conv3.weight", "", pre + ".bn3", width, outp, 1, 1, Ho, 0, 1);
-            add_conv_op(c3, fr[1], fr[0], idbuf);  // conv1's buffer is free again
+            if (fuse) {
+                e->convs[c3].fuse_ds = cd;
+                add_conv_op(c3, fr[1], fr[0], -1);
+                e->ops.back().in2_buf = cur;
+                e->ops.back().macs_per_clip += 8.0 * Ho * Ho * (double)outp * inplanes;
+            } else {
+                add_conv_op(c3, fr[1], fr[0], idbuf);  // conv1's buffer is free again
+            }
             cur = fr[0];
             H = Ho;
             inplanes = outp;
@@ -507,6 +530,7 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     }
     p.tiles_w = (AMODE == wd::A_STRIP || AMODE == wd::A_TAP) ? std::max(1, a.Wout / wd::kStripPixels) : 1;
     p.tap_bh = (AMODE == wd::A_TAP && a.Wout == 7) ? 2 : 1;
+    p.kb_split = c.kb_split;
     // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
     p.prefetch_kblocks = (g_prefetch_kblocks >= 0) ? g_prefetch_kblocks : ((sp.a_stages <= 3 && a.kblocks >= 4) ? 4 : 0);
     p.trace = g_trace;
@@ -550,7 +574,7 @@ int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 4;  // cta_group::2 k
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
     // 256-wide tiles only: the BN = 128 instantiation of conv_2cta_kernel faults on the device (not a barrier
     // time-out; cause not found in round 1) and is not dispatched.
-    if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0) return false;
+    if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0 || c.kb_split > 0) return false;
     if (a.residual != nullptr)  // conv3 of layers 3-4 (K >= 256): pair kernel with the in-place residual epilogue
         return g_2cta >= 4 && c.a_mode == wd::A_TMA && a.kblocks >= 4 && a.fold == 0;
     if (c.a_mode == wd::A_TMA) return a.kblocks >= 4 && (a.fold == 0 || a.fold % 64 == 0);
@@ -692,6 +716,9 @@ int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
 
 int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st) {
     if (version >= 3) return launch_v4(c, a, sm_count, st);
+    if (c.kb_split > 0)
+        return fail(WD_ERR_INVALID, "%s runs with the downsample fused into its K dimension: needs the v4 kernel "
+                    "(create the engine with WD_FUSE_DS=0 to use older generations)", c.name.c_str());
     if (version == 2) return launch_v3(c, a, sm_count, st);
     if (c.a_mode == wd::A_STRIP) return fail(WD_ERR_INVALID, "strip mode needs the v3/v4 kernel");
     if (version == 1) return launch_persist(c, a, sm_count, st);
@@ -1067,6 +1094,8 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->desc = *d;
     e->sm_count = prop.multiProcessorCount;
     e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
+    e->fuse_ds_requested = getenv("WD_FUSE_DS") ? atoi(getenv("WD_FUSE_DS")) : 1;
+    e->fuse_ds = e->fuse_ds_requested;
     int r = build_plan(e);
     if (r != WD_OK) {
         delete e;
@@ -1152,6 +1181,23 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
         *out = it->second->data;
         return WD_OK;
     };
+    // The op plan depends on two options that may have changed since wd_engine_create: folding the stride-1
+    // downsample into conv3 needs the v4 kernel and the TMA A path.  Rebuild the plan when they disagree.
+    {
+        const int want_fuse = (e->fuse_ds_requested && e->use_tma_a && e->persistent >= 3) ? 1 : 0;
+        if (want_fuse != e->fuse_ds) {
+            for (auto& c : e->convs) {
+                if (c.w_packed) cudaFree(c.w_packed);
+                if (c.bias) cudaFree(c.bias);
+            }
+            e->convs.clear();
+            e->ops.clear();
+            e->fuse_ds = want_fuse;
+            e->tap_idx = -1;
+            WD_TRY(build_plan(e));
+        }
+    }
+    std::map<int, std::vector<float>> folded_w, folded_shift;
     for (ConvLayer& c : e->convs) {
         const int64_t wn = (int64_t)c.Cout * c.Cin * c.k * c.k;
         const float* w = nullptr;
@@ -1169,6 +1215,34 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             const float s = g[i] / std::sqrt(var[i] + 1e-5f);
             scale[i] = s;
             shift[i] = b[i] - mu[i] * s;
+        }
+        if (c.fused_away) {  // a 1x1 downsample that runs inside its block's conv3: keep the folded weights for it
+            std::vector<float>& fw = folded_w[&c - e->convs.data()];
+            fw.resize((size_t)c.Cout * c.Cin);
+            for (int co = 0; co < c.Cout; ++co)
+                for (int ci = 0; ci < c.Cin; ++ci) fw[(size_t)co * c.Cin + ci] = w[(size_t)co * c.Cin + ci] * scale[co];
+            folded_shift[&c - e->convs.data()] = shift;
+            continue;
+        }
+        if (c.fuse_ds >= 0) {  // conv3 + downsample as one GEMM: K = [conv3 channels | block-input channels]
+            const ConvLayer& d = e->convs[c.fuse_ds];
+            const std::vector<float>& dw = folded_w[c.fuse_ds];
+            const std::vector<float>& dshift = folded_shift[c.fuse_ds];
+            const int K3 = c.Cin, Kd = d.Cin;
+            std::vector<float> wcat((size_t)c.Cout * (K3 + Kd)), ones(c.Cout, 1.0f), bsum(c.Cout);
+            for (int co = 0; co < c.Cout; ++co) {
+                for (int ci = 0; ci < K3; ++ci) wcat[(size_t)co * (K3 + Kd) + ci] = w[(size_t)co * K3 + ci] * scale[co];
+                for (int ci = 0; ci < Kd; ++ci) wcat[(size_t)co * (K3 + Kd) + K3 + ci] = dw[(size_t)co * Kd + ci];
+                bsum[co] = shift[co] + dshift[co];
+            }
+            c.Cin = K3 + Kd;  // pack as a 1x1 convolution over the concatenated channels ...
+            const int rc = upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, wcat.data(), ones.data(), bsum.data(),
+                                       e->persistent >= 2 ? e->use_strip : 0, e->persistent >= 3);
+            c.Cin = K3;       // ... the layer itself keeps its own channel count (A map geometry)
+            c.kb_split = K3 / 64;
+            WD_TRY(rc);
+            if (c.a_mode != wd::A_TMA) return fail(WD_ERR_INVALID, "%s: fused downsample needs the TMA A path", c.name.c_str());
+            continue;
         }
         WD_TRY(upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, w, scale.data(), shift.data(),
                            e->persistent >= 2 ? e->use_strip : 0, e->persistent >= 3));
@@ -1194,6 +1268,9 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
             if (c.fold == 32)
                 WD_TRY(make_amap32(&c.amap32, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
+            if (o.in2_buf >= 0)  // fused downsample: second A source = the block input (the amap32 slot is free: fold 0)
+                WD_TRY(make_amap(&c.amap32, e->buf[o.in2_buf], e->convs[c.fuse_ds].Cin,
+                                 (size_t)e->desc.max_clips * c.Hin * c.Win));
         }
     }
     const float *fw, *fb;
