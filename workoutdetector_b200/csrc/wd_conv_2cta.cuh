@@ -126,6 +126,7 @@ struct Conv2CtaArgs {
     int prefetch;       // L2-prefetch distance of the A operand in k-blocks (0 = off)
     // TAP variant (A_TAP boxes, 112-row tiles; see wd_conv_v4.cuh): geometry of the convolution
     int Hout, Wout, S, stride, pad, cin_blocks, tiles_w, tap_bh, num_m;  // num_m = ceil(M / 112)
+    int kb_split, stride2;  // TAP: fused stride-2 downsample — k-blocks >= kb_split come from the second A map (`rmap` slot)
 };
 
 // TAP = false: 1x1 stride-1 (one 3-D A box of 128 rows per k-block, TemporalShift = box t coordinate).
@@ -176,6 +177,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 mbar_init(&tmem_full_bar[s], 1);
                 mbar_init(&tmem_empty_bar[s], 16);
             }
+            if (TAP && a.kb_split > 0) tma_prefetch_desc(&rmap);
             if (RES) {
                 tma_prefetch_desc(&rmap);
                 for (int s = 0; s < 24; ++s) mbar_init(&bars[192 + s], 1);
@@ -350,9 +352,14 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                         tma_load_2d_2cta(&wmap128, leader_full, stage + kATileBytes, kb * kTileK, cta_n0 + (int)rank * (BN / 2));
                     } else if (TAP) {
                         const int rows_per_box = kStripRows / a.tap_bh;
+                        const bool second = a.kb_split > 0 && kb >= a.kb_split;
+                        const CUtensorMap* mp = second ? &rmap : &amap;
+                        const int st2 = second ? a.stride2 : a.stride;
+                        const int cc = (second ? kb - a.kb_split : cb) * kTileK;
                         for (int j = 0; j < a.tap_bh; ++j)
-                            tma_load_5d_2cta(&amap, leader_full, stage + j * rows_per_box * 128, cb * kTileK, 0,
-                                             tow * a.stride + tap_s - a.pad, toh[j] * a.stride + tap_r - a.pad, tn[j]);
+                            tma_load_5d_2cta(mp, leader_full, stage + j * rows_per_box * 128, cc, 0,
+                                             tow * st2 + (second ? 0 : tap_s - a.pad),
+                                             toh[j] * st2 + (second ? 0 : tap_r - a.pad), tn[j]);
                     } else {
                         const int c = kb * kTileK;
                         int dt = 0;

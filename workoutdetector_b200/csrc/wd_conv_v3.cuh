@@ -39,7 +39,8 @@ struct ConvArgs3 {
     int a_stage_bytes;
     int off_b, off_out, off_res, off_bar;  // byte offsets from the 1024-aligned base (A ring at 0)
     int tiles_w;     // strip / tap mode: 14-pixel segments per image row
-    int kb_split;    // v4 A_TMA: k-blocks >= kb_split (> 0) come from the second A map (fused downsample)
+    int kb_split;    // v4: k-blocks >= kb_split (> 0) come from the second A map (fused downsample)
+    int stride2;     // tap mode: pixel stride of the second A map (2 for the stride-2 downsamples)
     int w_group;     // v4: (A stage, tap) steps per W stage (W ring entries are w_group tiles)
     int tap_bh;      // tap mode: image rows per tile (2 for 7-pixel rows, else 1)
     int prefetch_kblocks;  // v4: L2-prefetch the A operand this many k-blocks ahead (0 = off)

@@ -125,7 +125,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
             if (kTmaA) tma_prefetch_desc(&amap);
             if (HAS_RES) tma_prefetch_desc(&rmap);
             if (k112) tma_prefetch_desc(&omap16);
-            if (AMODE == A_TMA && (a.fold == 32 || p.kb_split > 0)) tma_prefetch_desc(&amap32);
+            if ((AMODE == A_TMA && (a.fold == 32 || p.kb_split > 0)) || (kTap && p.kb_split > 0)) tma_prefetch_desc(&amap32);
             for (int s = 0; s < 8; ++s) {
                 mbar_init(&bars[s], merged ? 2 : (kStrip ? 3 : (kTmaA ? 1 : 128)));
                 mbar_init(&a_empty[s], 1);
@@ -562,9 +562,16 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                         } else if (kTap) {
                             mbar_arrive_expect_tx(&a_full[slot], kStripRows * 128);
                             const int rows_per_box = kStripRows / p.tap_bh;
+                            // fused stride-2 downsample (1x1 conv3 of block 0): k-blocks >= kb_split read the block
+                            // input through the second map at twice the output coordinates
+                            const bool second = p.kb_split > 0 && as >= p.kb_split;
+                            const CUtensorMap* mp = second ? &amap32 : &amap;
+                            const int st = second ? p.stride2 : a.stride;
+                            const int cc = (second ? as - p.kb_split : cb) * kTileK;
                             for (int j = 0; j < p.tap_bh; ++j)
-                                tma_load_5d(&amap, &a_full[slot], dst + j * rows_per_box * 128, cb * kTileK, 0,
-                                            tow * a.stride + tap_s - a.pad, toh[j] * a.stride + tap_r - a.pad, tn[j]);
+                                tma_load_5d(mp, &a_full[slot], dst + j * rows_per_box * 128, cc, 0,
+                                            tow * st + (second ? 0 : tap_s - a.pad), toh[j] * st + (second ? 0 : tap_r - a.pad),
+                                            tn[j]);
                         } else if (p.kb_split > 0 && as >= p.kb_split) {  // fused downsample: block-input channels
                             mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
                             tma_load_3d(&amap32, &a_full[slot], dst, (as - p.kb_split) * kTileK, 0, px0);

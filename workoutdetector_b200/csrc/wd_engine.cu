@@ -110,7 +110,8 @@ struct ConvLayer {
     int Hin = 0, Win = 0, Hout = 0, Wout = 0;
     int fold = 0, relu = 0;
     bool stem = false;
-    int fuse_ds = -1;       // conv3 of a stride-1 block 0: index of the downsample conv folded into its K dimension
+    int fuse_stride = 1;    // stride of the folded downsample (2: the second A source is sampled at every other pixel)
+    int fuse_ds = -1;       // conv3 of a block 0: index of the downsample conv folded into its K dimension
     bool fused_away = false; // downsample conv that runs inside the block's conv3 (kept for its weights)
     int kb_split = 0;       // fused conv3: k-blocks [0, kb_split) come from the block's conv2 output, the rest from the
                             // block input (second A map)
@@ -150,8 +151,8 @@ struct wd_engine {
     int tile_n_max = 256;
     int persistent = 3;  // 0: one tile per CTA, 1: persistent v2, 2: v3 (W-resident, strip 3x3), 3: v4 (uniform MMA issue)
     int use_strip = 1;
-    int fuse_ds = 1;         // fold the stride-1 downsample (layer1.0) into conv3's K dimension (current plan)
-    int fuse_ds_requested = 1;  // WD_FUSE_DS at create time
+    int fuse_ds = 2;
+    int fuse_ds_requested = 2;  // WD_FUSE_DS at create time
     int stem_seg_rows = 28;  // pooled rows per work unit of the fused stem + max-pool kernel
     int sm_count = 148;
     std::vector<ConvLayer> convs;
@@ -274,7 +275,7 @@ int build_plan(wd_engine* e) {
             // Block 0 of layer 1 (stride 1): out = relu(W3*y2 + b3 + Wd*x + bd) is ONE GEMM over the concatenated
             // K = [y2 | x] with weights [W3 | Wd] and bias b3 + bd — the 1.6 MB/frame downsample output is never written
             // or read back as a residual (bf16 mode; FP32_VALIDATE keeps the reference's op sequence).
-            const bool fuse = (b == 0 && stride == 1 && e->desc.mode == WD_MODE_BF16 && e->fuse_ds);
+            const bool fuse = (b == 0 && e->desc.mode == WD_MODE_BF16 && (stride == 1 ? e->fuse_ds >= 1 : e->fuse_ds >= 2));
             int cd = -1;
             if (b == 0) {
                 cd = add_conv(nm + ".downsample", pre + ".downsample.0.weight", "", pre + ".downsample.1", inplanes, outp,
@@ -290,6 +291,7 @@ int build_plan(wd_engine* e) {
                 add_conv(nm + ".conv3", pre + ".conv3.weight", "", pre + ".bn3", width, outp, 1, 1, Ho, 0, 1);
             if (fuse) {
                 e->convs[c3].fuse_ds = cd;
+                e->convs[c3].fuse_stride = stride;
                 add_conv_op(c3, fr[1], fr[0], -1);
                 e->ops.back().in2_buf = cur;
                 e->ops.back().macs_per_clip += 8.0 * Ho * Ho * (double)outp * inplanes;
@@ -531,6 +533,7 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.tiles_w = (AMODE == wd::A_STRIP || AMODE == wd::A_TAP) ? std::max(1, a.Wout / wd::kStripPixels) : 1;
     p.tap_bh = (AMODE == wd::A_TAP && a.Wout == 7) ? 2 : 1;
     p.kb_split = c.kb_split;
+    p.stride2 = c.fuse_ds >= 0 ? c.fuse_stride : 1;
     // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
     p.prefetch_kblocks = (g_prefetch_kblocks >= 0) ? g_prefetch_kblocks : ((sp.a_stages <= 3 && a.kblocks >= 4) ? 4 : 0);
     p.trace = g_trace;
@@ -574,7 +577,7 @@ int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 4;  // cta_group::2 k
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
     // 256-wide tiles only: the BN = 128 instantiation of conv_2cta_kernel faults on the device (not a barrier
     // time-out; cause not found in round 1) and is not dispatched.
-    if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0 || c.kb_split > 0) return false;
+    if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0 || (c.kb_split > 0 && c.a_mode != wd::A_TAP)) return false;
     if (a.residual != nullptr)  // conv3 of layers 3-4 (K >= 256): pair kernel with the in-place residual epilogue
         return g_2cta >= 4 && c.a_mode == wd::A_TMA && a.kblocks >= 4 && a.fold == 0;
     if (c.a_mode == wd::A_TMA) return a.kblocks >= 4 && (a.fold == 0 || a.fold % 64 == 0);
@@ -605,6 +608,8 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     p.Hout = a.Hout; p.Wout = a.Wout; p.S = a.S; p.stride = a.stride; p.pad = a.pad; p.cin_blocks = a.cin_blocks;
     p.tiles_w = std::max(1, a.Wout / wd::kStripPixels);
     p.tap_bh = (TAP && a.Wout == 7) ? 2 : 1;
+    p.kb_split = c.kb_split;
+    p.stride2 = c.fuse_ds >= 0 ? c.fuse_stride : 1;
     int pairs = std::min(p.num_tiles, sm_count / 2);
     pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);  // a pair keeps one n-tile (bias)
     cudaLaunchConfig_t cfg{};
@@ -807,6 +812,8 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
         return fail(WD_ERR_INVALID, "%s: Cout=%d not divisible by tile %d", c.name.c_str(), c.Cout, c.tile_n);
     if (c.stem)
         c.a_mode = wd::A_STEM;
+    else if (c.fuse_ds >= 0 && c.fuse_stride == 2)
+        c.a_mode = wd::A_TAP;  // conv3 + stride-2 downsample: both A sources as 14-pixel tap boxes
     else if (use_tma_a && c.k == 1 && c.stride == 1 && (c.fold == 0 || c.fold % 64 == 0 || (c.fold == 32 && g_fold32_tma && v4)))
         c.a_mode = wd::A_TMA;
     else if (use_strip && c.k == 3 && c.stride == 1 && c.Wout % wd::kStripPixels == 0 && c.Wout >= wd::kStripPixels)
@@ -1094,7 +1101,7 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->desc = *d;
     e->sm_count = prop.multiProcessorCount;
     e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
-    e->fuse_ds_requested = getenv("WD_FUSE_DS") ? atoi(getenv("WD_FUSE_DS")) : 1;
+    e->fuse_ds_requested = getenv("WD_FUSE_DS") ? atoi(getenv("WD_FUSE_DS")) : 2;  // 0 off, 1 layer1.0, 2 + the stride-2 blocks
     e->fuse_ds = e->fuse_ds_requested;
     int r = build_plan(e);
     if (r != WD_OK) {
@@ -1184,7 +1191,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     // The op plan depends on two options that may have changed since wd_engine_create: folding the stride-1
     // downsample into conv3 needs the v4 kernel and the TMA A path.  Rebuild the plan when they disagree.
     {
-        const int want_fuse = (e->fuse_ds_requested && e->use_tma_a && e->persistent >= 3) ? 1 : 0;
+        const int want_fuse = (e->use_tma_a && e->persistent >= 3) ? e->fuse_ds_requested : 0;
         if (want_fuse != e->fuse_ds) {
             for (auto& c : e->convs) {
                 if (c.w_packed) cudaFree(c.w_packed);
@@ -1241,7 +1248,8 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             c.Cin = K3;       // ... the layer itself keeps its own channel count (A map geometry)
             c.kb_split = K3 / 64;
             WD_TRY(rc);
-            if (c.a_mode != wd::A_TMA) return fail(WD_ERR_INVALID, "%s: fused downsample needs the TMA A path", c.name.c_str());
+            if (c.a_mode != wd::A_TMA && c.a_mode != wd::A_TAP)
+                return fail(WD_ERR_INVALID, "%s: fused downsample needs the TMA / tap A path", c.name.c_str());
             continue;
         }
         WD_TRY(upload_conv(c, e->desc.mode, e->tile_n_max, e->use_tma_a, w, scale.data(), shift.data(),
@@ -1263,12 +1271,18 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
                 WD_TRY(make_amap_tap(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips, c.stride,
                                      c.Wout == 7 ? 7 : wd::kStripPixels));
+                if (o.in2_buf >= 0) {  // fused stride-2 downsample: the block input at twice the resolution
+                    const ConvLayer& d = e->convs[c.fuse_ds];
+                    WD_TRY(make_amap_tap(&c.amap32, e->buf[o.in2_buf], d.Cin, d.Win, d.Hin, (size_t)e->desc.max_clips,
+                                         d.stride, c.Wout == 7 ? 7 : wd::kStripPixels));
+                    c.rmap = c.amap32;  // the CTA-pair kernel takes the second A map in its (unused) residual slot
+                }
             }
             if (c.a_mode != wd::A_TMA) continue;
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
             if (c.fold == 32)
                 WD_TRY(make_amap32(&c.amap32, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
-            if (o.in2_buf >= 0)  // fused downsample: second A source = the block input (the amap32 slot is free: fold 0)
+            if (o.in2_buf >= 0 && c.a_mode == wd::A_TMA)  // fused downsample: second A source = the block input (amap32 slot)
                 WD_TRY(make_amap(&c.amap32, e->buf[o.in2_buf], e->convs[c.fuse_ds].Cin,
                                  (size_t)e->desc.max_clips * c.Hin * c.Win));
         }
