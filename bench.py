@@ -235,16 +235,18 @@ def main():
     conv_ms = sum(m for m, o in zip(op_ms, ops) if o["kind"] in ("conv", "stem", "stem_pool"))
     conv_flops = sum(2.0 * o["macs_per_clip"] * B for o in ops if o["kind"] in ("conv", "stem", "stem_pool"))
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    n_tc = sum(1 for o in ops if o["kind"] in ("conv", "stem", "stem_pool"))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")   # dram bytes of the same launches from the ncu pass
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_step")
-    # "launch" here = the 53 tcgen05 launches of one step taken together (52 convolutions + stem_pool_kernel):
+    # "launch" here = the tcgen05 launches of one step taken together (48 convolutions, the four block-0 downsamples
+    # folded into their conv3's K dimension, + stem_pool_kernel = 49):
     # achieved = their algorithmic FLOPs / the sum of their CUDA-event durations; traffic = their summed DRAM bytes.
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["sustained"], traffic=traffic,
-                    kernel="the 53 tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), stem_pool_kernel",
+                    kernel=f"the {n_tc} tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), stem_pool_kernel",
                     frac_of_burst=achieved / peaks["burst"], peak_source=peaks["source"],
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / max(sum(op_ms), 1e-9),
                     dram_gbs=(traffic / (conv_ms * 1e-3) / 1e9) if traffic else None,
