@@ -32,7 +32,10 @@ typedef enum wd_status {
     WD_ERR_UNSUPPORTED = -5  /* device is not sm_100 */
 } wd_status;
 
-typedef enum wd_arch { WD_ARCH_TSM_R50 = 0 } wd_arch;
+typedef enum wd_arch {
+    WD_ARCH_TSM_R50 = 0, /* workoutdetector/models/tsm.py */
+    WD_ARCH_TDN_R50 = 1  /* workoutdetector/models/tdn.py + tsn.py (5 frames per segment) */
+} wd_arch;
 
 typedef enum wd_mode {
     WD_MODE_BF16 = 0,         /* product path: bf16 operands, fp32 accumulate on tcgen05 */
@@ -96,9 +99,20 @@ int wd_preprocess_u8(wd_engine* e, const uint8_t* frames_hwc, int n_src, int H, 
  * [n_frames, 3, 224, 224], already normalised -> [n_frames] engine frames. */
 int wd_pack_nchw_f32(wd_engine* e, const float* x_nchw, int n_frames, void* out_frames, void* stream);
 
+/* TDN input.  A preprocessed TDN clip is 8 centre frames (engine frames, above) plus the space-to-depth tensor of the
+ * pooled frame differences [56, 56, 8, 64] (bf16 / fp32); for a batch of n clips the buffer holds the n*8 centre frames
+ * first and the n difference tensors after them.  wd_engine_clip_bytes = bytes per clip of that buffer (for TSM:
+ * 8 * wd_engine_frame_bytes).
+ * wd_pack_tdn_f32 replaces the head of TDN_Net.forward (models/tdn.py:139-150: frame slicing, the four differences,
+ * avg_diff) for what the reference module takes: device fp32 [n_clips, 8, 5, 3, 224, 224] (== [n_clips*8, 15, 224, 224],
+ * tsn.py:337-338), already normalised.  Differences are formed in fp32 before anything is rounded to bf16. */
+size_t wd_engine_clip_bytes(const wd_engine* e);
+int wd_pack_tdn_f32(wd_engine* e, const float* x, int n_clips, void* out_clips, void* stream);
+
 /* Replaces TSM.forward (tsm.py:409-419) + to_softmax (utils/visualize.py:140-150) + the arg-max / threshold of
  * utils/eval.py:159-164.
- *   frames : device [n_clips*8] engine frames, frame index = clip*8 + segment
+ *   frames : device [n_clips*8] engine frames, frame index = clip*8 + segment (TDN: the buffer wd_pack_tdn_f32 wrote;
+ *            the call then replaces TSN.forward, tsn.py:335-351, around TDN_Net.forward, tdn.py:139-178)
  *   logits : device fp32 [n_clips, num_class] (raw consensus scores, what the reference module returns)
  *   probs  : device fp32 [n_clips, num_class] or NULL
  *   state  : device int32 [n_clips] or NULL; arg-max class (first index on ties) if its score >= threshold
@@ -135,7 +149,8 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, 
 
 /* ---- introspection, tuning and test hooks (not part of the reference surface) ---- */
 int wd_engine_num_ops(const wd_engine* e);
-/* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head, 4 fused stem conv + maxpool), Cin, Cout, ksize, stride, Hout, Wout, fold,
+/* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head, 4 fused stem conv + maxpool, 5 blend with up-sampled
+ *              tensor (TDN), 6 motion excitation + temporal Conv1d (TDN)), Cin, Cout, ksize, stride, Hout, Wout, fold,
  *              a_mode (0 gather, 1 stem, 2 tma, 3 strip, -1 n/a), tile_n;   macs_per_clip = multiply-accumulates per clip */
 int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int32_t* info, double* macs_per_clip);
 /* After op `idx` runs in the next forwards, its output is converted to fp32 NCHW frames [n_clips*8, C, H, W]

@@ -10,6 +10,8 @@ runs the reference functions on seeded inputs, asserts that oracle/*.py reproduc
   tests/golden/tsm_golden.npz       logits of the reference TSM module for two weight sets x seeded clips, sampled
                                     per-op activations, weight checksums, preprocessing samples
   tests/golden/eval_golden.json     obo_mae / RepcountHelper.eval_count / to_softmax outputs of the reference
+  tests/golden/tdn_golden.npz       logits + hooked activations of the reference TDN module (tdn.create_model) for a
+                                    seeded state_dict and seeded [B,8,5,3,224,224] inputs
 
 Usage:  python oracle/gen_golden.py            (from the repo root)
 """
@@ -259,6 +261,57 @@ def gen_inference_path(ref_ic, ref_tsm, ref_build, ort, out_arrays):
     out_arrays["window_quirk_logits"] = ref.numpy().copy()
 
 
+def gen_tdn(ref_tdn, out):
+    """TDN-R50: reference module vs oracle/tdn_oracle.py on a seeded state_dict."""
+    from oracle import tdn_oracle as T
+    orig = ref_tdn.fbresnet50   # no checkpoint file here: pretrained=True -> random init of the same architecture
+    ref_tdn.fbresnet50 = lambda num_segments=8, pretrained=False, num_classes=1000: orig(num_segments, False, num_classes)
+    torch.manual_seed(0)
+    model = ref_tdn.create_model(num_class=12, num_segments=8, base_model="resnet50")
+    model.train(False)
+    sd = T.random_state_dict(12, 5)
+    ref_keys = list(model.state_dict().keys())
+    assert ref_keys == list(sd.keys()), [k for k in ref_keys if k not in sd][:5] + [k for k in sd if k not in ref_keys][:5]
+    model.load_state_dict(sd, strict=True)
+    x = T.golden_input()   # clip 0 noise, clip 1 temporally smooth frames
+    got = {}
+    bm = model.base_model
+    hooks = [
+        bm.maxpool_diff.register_forward_hook(lambda m, i, o: got.__setitem__("maxpool_diff", o)),
+        bm.resnext_layer1.register_forward_hook(lambda m, i, o: got.__setitem__("diff1.2.conv3", o)),
+        bm.layer1_bak.register_forward_hook(lambda m, i, o: got.__setitem__("layer1.2.conv3", o)),
+        bm.layer1_bak[0].register_forward_pre_hook(lambda m, i: got.__setitem__("fuse1", i[0])),
+        bm.layer2_bak[0].register_forward_pre_hook(lambda m, i: got.__setitem__("fuse2", i[0])),
+        bm.layer2_bak[0].shift.register_forward_hook(lambda m, i, o: got.__setitem__("layer2.0.mse", o)),
+        bm.layer3_bak[2].shift.register_forward_hook(lambda m, i, o: got.__setitem__("layer3.2.mse", o)),
+        bm.layer4_bak[1].shift.register_forward_hook(lambda m, i, o: got.__setitem__("layer4.1.mse", o)),
+        bm.layer4_bak.register_forward_hook(lambda m, i, o: got.__setitem__("layer4.2.conv3", o)),
+    ]
+    with torch.no_grad():
+        y_ref = model(x)
+        y_flat = model(x.reshape(-1, 3, 224, 224))          # the other accepted input form (tdn.py:141-145)
+        taps = {}
+        y_or = T.tdn_forward(sd, x, tap=lambda n, t: taps.__setitem__(n, t))
+        y_emu = T.tdn_forward(sd, x, emulate_bf16=True)
+    for h in hooks:
+        h.remove()
+    assert torch.equal(y_ref, y_flat)
+    d = float((y_ref - y_or).abs().max())
+    assert d < 2e-5 * max(1.0, float(y_ref.abs().max())), d
+    arrays = {"logits": y_ref.numpy().copy(), "wsum": np.array([float(sum(v.double().abs().sum() for v in sd.values()))])}
+    for k, v in got.items():
+        dd = float((v - taps[k]).abs().max()) / float(v.abs().max())
+        assert dd < 1e-5, (k, dd)
+        arrays["act_" + k] = v[::8, ::max(1, v.shape[1] // 8), ::max(1, v.shape[2] // 4), ::max(1, v.shape[3] // 4)].numpy().copy()
+    probs = torch.softmax(y_ref, 1)
+    print(f"tdn: {len(sd)} tensors load strict; oracle vs reference module max abs diff {d:.3g} (|logit| max "
+          f"{float(y_ref.abs().max()):.2f}); {len(got)} hooked activations match; bf16-emulation drift "
+          f"{float((y_emu - y_ref).abs().max()):.3g}, softmax drift {float((torch.softmax(y_emu, 1) - probs).abs().max()):.3g}; "
+          f"pmax {[round(float(p), 3) for p in probs.max(1).values]}")
+    np.savez_compressed(out, **arrays)
+    print(f"wrote {out} ({os.path.getsize(out) / 1024:.0f} KiB)")
+
+
 def gen_eval(ref_eval, ref_vis, ref_ds, out):
     from oracle import count_oracle as CO
     rng = np.random.RandomState(11)
@@ -299,6 +352,9 @@ def main():
     ref_vis = importlib.import_module("workoutdetector.utils.visualize")
     ref_ds = importlib.import_module("workoutdetector.datasets.repcount_dataset")
     torch.set_num_threads(os.cpu_count())
+    if "--tdn-only" in sys.argv:
+        gen_tdn(importlib.import_module("workoutdetector.models.tdn"), os.path.join(GOLD, "tdn_golden.npz"))
+        return
     gen_count(ref_ic, os.path.join(GOLD, "count_vectors.json"))
     gen_eval(ref_eval, ref_vis, ref_ds, os.path.join(GOLD, "eval_golden.json"))
     npz = os.path.join(GOLD, "tsm_golden.npz")
@@ -309,6 +365,7 @@ def main():
         arrays = {k: z[k] for k in z.files}
     arrays.update(extra)
     np.savez_compressed(npz, **arrays)
+    gen_tdn(importlib.import_module("workoutdetector.models.tdn"), os.path.join(GOLD, "tdn_golden.npz"))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,237 @@
+"""GPU (B200) parity tests for the TDN ResNet-50 path, through the C ABI, against
+oracle/tdn_oracle.py (pinned to the reference module by oracle/gen_golden.py) and tests/golden/tdn_golden.npz
+(logits and hooked activations of the reference's own TSN(TDN_Net) module).  Tolerances as in test_gpu_parity.py:
+softmax <= 1e-4 in the fp32 validation mode, <= 2e-2 in bf16."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tdn_oracle as T
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 2e-2
+TOL_FP32 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def tdn_sd():
+    return T.random_state_dict(12, 5)
+
+
+@pytest.fixture(scope="module")
+def tdn_gold(golden_dir):
+    with np.load(os.path.join(golden_dir, "tdn_golden.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def tdn_ref(tdn_sd):
+    """Oracle forward (reference arithmetic and the bf16 emulation) with every op's output."""
+    x = T.golden_input()
+    taps, taps_emu = {}, {}
+    with torch.no_grad():
+        y = T.tdn_forward(tdn_sd, x, tap=lambda n, t: taps.__setitem__(n, t))
+        y_emu = T.tdn_forward(tdn_sd, x, emulate_bf16=True, tap=lambda n, t: taps_emu.__setitem__(n, t))
+    return dict(x=x, logits=y, taps=taps, logits_emu=y_emu, taps_emu=taps_emu)
+
+
+@pytest.fixture(scope="module")
+def tdn_engines(tdn_sd):
+    from workoutdetector_b200.engine import Engine
+    made = {}
+
+    def get(mode, max_clips=2, **kw):
+        key = (mode, max_clips, tuple(sorted(kw.items())))
+        if key not in made:
+            e = Engine(12, max_clips=max_clips, mode=mode, arch="tdn", **kw)
+            e.load_state_dict(tdn_sd)
+            made[key] = e
+        return made[key]
+
+    yield get
+    for e in made.values():
+        e.close()
+
+
+def _run_taps(engine, clips, n_clips, taps_ref, tol, tol_mse=None):
+    worst = ("", 0.0)
+    for op in engine.ops():
+        if op["kind"] == "head":
+            continue
+        t = engine.set_tap(op["index"], n_clips)
+        engine.forward(clips)
+        torch.cuda.synchronize()
+        ref = taps_ref[op["name"]]
+        err = float((t.cpu() - ref).abs().max()) / (float(ref.abs().max()) + 1e-6)
+        if err > worst[1]:
+            worst = (op["name"], err)
+        assert err < (tol_mse if (tol_mse and op["kind"] == "mse") else tol), (op["name"], op["kind"], op["a_mode"], err)
+    engine.set_tap(-1)
+    return worst
+
+
+def test_oracle_matches_reference_golden(tdn_ref, tdn_gold):
+    """The oracle run on this box reproduces what the reference module produced in the build container."""
+    ref = torch.from_numpy(tdn_gold["logits"])
+    assert float((tdn_ref["logits"] - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_pack_tdn_layout(tdn_engines, tdn_ref, mode):
+    """wd_pack_tdn_f32: centre frames + space-to-depth pooled differences (tdn.py:146-150)."""
+    e = tdn_engines(mode)
+    x = tdn_ref["x"]
+    buf = e.pack_tdn(x.cuda())
+    torch.cuda.synchronize()
+    esz = buf.element_size()
+    n_fr = 2 * 8 * e.frame_shape[0] * e.frame_shape[1] * e.frame_shape[2]
+    frames = buf[:n_fr].view((16,) + e.frame_shape)
+    centre = x.reshape(16, 15, 224, 224)[:, 6:9].permute(0, 2, 3, 1)
+    got = e.image_view(frames).float().cpu()
+    tol = 0.0 if mode == "fp32" else 2 ** -8
+    assert float((got - centre).abs().max()) <= tol * float(centre.abs().max())
+    if e.frame_pad:
+        assert float(frames[:, :, :e.frame_pad].abs().max()) == 0 and float(frames[..., 3].abs().max()) == 0
+    d = buf[n_fr:].view(2, 56, 56, 8, 2, 2, 16).float().cpu()       # [clip, Y, X, t, py, px, ch]
+    assert buf.numel() * esz == 2 * e.clip_bytes
+    ref = T.diff_input(x.reshape(16, 15, 224, 224)).view(2, 8, 12, 56, 2, 56, 2)   # [clip, t, ch, Y, py, X, px]
+    ref = ref.permute(0, 3, 5, 1, 4, 6, 2)
+    assert float(d[..., 12:].abs().max()) == 0
+    err = float((d[..., :12] - ref).abs().max())
+    assert err <= (1e-6 if mode == "fp32" else 2 ** -8 * float(ref.abs().max())), err
+
+
+def test_tdn_fp32_validation_mode(tdn_engines, tdn_ref, tdn_gold):
+    """fp32 mode: every op against the oracle's reference arithmetic; logits / softmax against the REFERENCE module's
+    golden output within 1e-4."""
+    e = tdn_engines("fp32")
+    kinds = {o["kind"] for o in e.ops()}
+    assert {"stem", "maxpool", "conv", "blend", "mse", "head"} <= kinds
+    clips = e.pack_tdn(tdn_ref["x"].cuda())
+    _run_taps(e, clips, 2, tdn_ref["taps"], 3e-5)
+    logits, probs, state = e.forward(clips)
+    ref = torch.from_numpy(tdn_gold["logits"])
+    assert float((logits.cpu() - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((probs.cpu() - F.softmax(ref, 1)).abs().max()) < TOL_FP32
+    assert torch.equal(state.cpu().long(), torch.where(F.softmax(ref, 1).max(1).values >= 0.5, ref.argmax(1), -1))
+
+
+def test_tdn_bf16_ops_vs_bf16_emulation(tdn_engines, tdn_ref, tdn_gold, tdn_sd):
+    """bf16 product path op by op against the oracle's bf16 emulation, logits / softmax against the reference golden."""
+    e = tdn_engines("bf16")
+    ops = e.ops()
+    assert sum(o["kind"] == "mse" for o in ops) == 13 and sum(o["kind"] == "blend" for o in ops) == 2
+    assert {"tma", "strip", "tap", "gather"} <= {o["a_mode"] for o in ops}
+    clips = e.pack_tdn(tdn_ref["x"].cuda())
+    # whole chain: the gate is a sigmoid of temporal DIFFERENCES of squeezed features, which amplifies the upstream
+    # one-ulp rounding-order noise, so the chained comparison is loose for those ops and each one is re-checked below
+    # in isolation, on the engine's own bf16 input, to one bf16 ulp
+    worst = _run_taps(e, clips, 2, tdn_ref["taps_emu"], 5e-2, tol_mse=0.15)
+    print("worst op", worst)
+    sdf = {k: v.float() for k, v in tdn_sd.items() if v.is_floating_point()}
+    for i, o in enumerate(ops):
+        if o["kind"] != "mse":
+            continue
+        assert ops[i - 1]["name"] == o["name"].replace(".mse", ".conv1")
+        xin = e.set_tap(i - 1, 2)
+        e.forward(clips)
+        torch.cuda.synchronize()
+        xin = xin.cpu().clone()
+        got = e.set_tap(i, 2)
+        e.forward(clips)
+        torch.cuda.synchronize()
+        L, b = o["name"].split(".")[0][-1], o["name"].split(".")[1]
+        p = f"base_model.layer{L}_bak.{b}"
+        with torch.no_grad():
+            want = T.shift_module(sdf, p + ".shift", T.mse_module(sdf, p + ".mse", xin))
+        err = float((got.cpu() - want).abs().max()) / float(want.abs().max())
+        assert err < 2 ** -7, (o["name"], err)
+    e.set_tap(-1)
+    logits, probs, state = e.forward(clips)
+    assert float((logits.cpu() - tdn_ref["logits_emu"]).abs().max()) < 5e-2
+    ref = torch.from_numpy(tdn_gold["logits"])
+    assert float((probs.cpu() - F.softmax(ref, 1)).abs().max()) < TOL_BF16
+    assert torch.equal(state.cpu().long(), ref.argmax(1))
+
+
+def test_tdn_golden_activations(tdn_engines, tdn_ref, tdn_gold):
+    """Sampled activations hooked on the reference module (maxpool_diff, fusions, motion excitation, layer outputs)."""
+    e = tdn_engines("fp32")
+    clips = e.pack_tdn(tdn_ref["x"].cuda())
+    names = {o["name"]: o["index"] for o in e.ops()}
+    for k, g in tdn_gold.items():
+        if not k.startswith("act_"):
+            continue
+        name = k[4:]
+        t = e.set_tap(names[name], 2)
+        e.forward(clips)
+        torch.cuda.synchronize()
+        v = t.cpu()
+        s = v[::8, ::max(1, v.shape[1] // 8), ::max(1, v.shape[2] // 4), ::max(1, v.shape[3] // 4)]
+        g = torch.from_numpy(g)
+        assert float((s - g).abs().max()) < 3e-5 * float(g.abs().max()), name
+    e.set_tap(-1)
+
+
+def test_tdn_module_dropin(tdn_sd, tdn_ref, tdn_gold):
+    """models.tdn.create_model / build_model: reference key layout, both input forms, reference golden logits."""
+    from types import SimpleNamespace
+    from workoutdetector_b200.models import build_model
+    from workoutdetector_b200.models.tdn import TSN, create_model
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    m = build_model(SimpleNamespace(model=Cfg(model_type="TDN", num_class=12, num_segments=8, base_model="resnet50")))
+    assert isinstance(m, TSN) and list(m.state_dict().keys()) == list(tdn_sd.keys())
+    m = create_model(num_class=12)
+    m.load_state_dict(tdn_sd, strict=True)
+    with pytest.raises(RuntimeError):
+        m(tdn_ref["x"])                      # CPU module: no fallback
+    m = m.to("cuda").eval()
+    x = tdn_ref["x"].cuda()
+    with torch.no_grad():
+        y6 = m(x)
+        y4 = m(x.reshape(-1, 3, 224, 224))
+    assert y6.shape == (2, 12) and torch.equal(y6, y4)
+    ref = torch.from_numpy(tdn_gold["logits"])
+    assert float((F.softmax(y6.cpu(), 1) - F.softmax(ref, 1)).abs().max()) < TOL_BF16
+    m.set_engine_mode("fp32")
+    with torch.no_grad():
+        y32 = m(x)
+    assert float((y32.cpu() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+def test_tdn_batch_composition_bit_exact(tdn_engines, tdn_ref):
+    """A clip's result does not depend on what else is in the batch (bf16 path, batch 5 vs 2)."""
+    e5 = tdn_engines("bf16", max_clips=5)
+    x = tdn_ref["x"]
+    g = torch.Generator().manual_seed(9)
+    xb = torch.cat([torch.randn(2, 8, 5, 3, 224, 224, generator=g), x[1:2], torch.randn(1, 8, 5, 3, 224, 224, generator=g),
+                    x[0:1]])
+    l5, _, _ = e5.forward(e5.pack_tdn(xb.cuda()))
+    l2, _, _ = e5.forward(e5.pack_tdn(x.cuda()))
+    l5b, _, _ = e5.forward(e5.pack_tdn(xb.cuda()))
+    assert torch.equal(l5, l5b)
+    assert torch.equal(l5[2], l2[1]) and torch.equal(l5[4], l2[0])
+
+
+def test_tdn_abi_errors(tdn_sd):
+    from workoutdetector_b200._lib import WdError
+    from workoutdetector_b200.engine import Engine
+    e = Engine(12, max_clips=1, arch="tdn")
+    with pytest.raises(WdError, match="before wd_engine_load_weights"):
+        e.forward(torch.zeros(e.clip_bytes // 2, dtype=torch.bfloat16, device="cuda"))
+    bad = {k: v for k, v in tdn_sd.items() if k != "base_model.layer3_bak.1.mse.conv3.weight"}
+    with pytest.raises(WdError, match="layer3_bak.1.mse.conv3.weight"):
+        e.load_state_dict(bad)
+    e.close()
+    from workoutdetector_b200._lib import check
+    tsm = Engine(12, max_clips=1)
+    with pytest.raises(WdError, match="TDN engine"):
+        check(tsm.lib.wd_pack_tdn_f32(tsm.h, None, 1, None, None))
+    tsm.close()

@@ -201,3 +201,26 @@ def test_two_rank_sharded_gather_gloo(tmp_path):
     for v in range(9):
         expect = [(v + w // 3) % 4 if w % 5 else -1 for w in range(lengths[v] // 8)]
         assert merged[f"video{v}"]["states"] == expect
+
+
+def test_tdn_module_state_dict_layout_matches_reference():
+    """models.tdn.create_model builds the reference's TSN(TDN_Net) key names, order and shapes (pinned by
+    oracle/gen_golden.py: the same seeded dict loads into the reference module with strict=True); 789 entries."""
+    from oracle import tdn_oracle as T
+    from workoutdetector_b200.models import tdn
+    m = tdn.create_model(num_class=12)
+    sd = T.random_state_dict(12, 5)
+    msd = m.state_dict()
+    assert list(msd.keys()) == list(sd.keys()) and len(sd) == 789
+    assert all(msd[k].shape == sd[k].shape for k in sd)
+    m.load_state_dict(sd, strict=True)
+    w = m.base_model.layer2_bak[0].shift.conv.weight        # 'shift' init pattern survives construction (tdn.py:352-358)
+    m2 = tdn.create_model(num_class=3)
+    w = m2.base_model.layer2_bak[0].shift.conv.weight
+    assert float(w[:16, 0, 2].min()) == 1 and float(w[16:32, 0, 0].min()) == 1 and float(w[32:, 0, 1].min()) == 1
+    assert float(w.sum()) == 128
+    assert torch.equal(m2.base_model.conv1_5[0].weight[:, 0], m2.base_model.conv1_temp.weight.mean(1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m2(torch.zeros(40, 3, 224, 224))
+    with pytest.raises(NotImplementedError):
+        tdn.create_model(num_class=3, num_segments=16)

@@ -166,3 +166,39 @@ def test_bf16_emulation_within_budget(weights):
     pa, _ = O.scores_to_states(a)
     pb, _ = O.scores_to_states(b)
     assert float((pa - pb).abs().max()) < 2e-2   # north_star: softmax within 2e-2 in bf16
+
+
+def test_tdn_oracle_vs_reference_golden(golden_dir):
+    """oracle/tdn_oracle.py against logits + hooked activations of the reference's TSN(TDN_Net) module."""
+    from oracle import tdn_oracle as T
+    with np.load(os.path.join(golden_dir, "tdn_golden.npz")) as z:
+        gold = {k: z[k] for k in z.files}
+    sd = T.random_state_dict(12, 5)
+    assert abs(float(sum(v.double().abs().sum() for v in sd.values())) - float(gold["wsum"][0])) < 1e-6 * gold["wsum"][0]
+    x = T.golden_input()[1:2]          # one clip keeps the CPU suite short
+    taps = {}
+    with torch.no_grad():
+        y = T.tdn_forward(sd, x, tap=lambda n, t: taps.__setitem__(n, t))
+        y40 = T.tdn_forward(sd, x.reshape(40, 3, 224, 224))
+    ref = torch.from_numpy(gold["logits"])[1:2]
+    assert torch.equal(y, y40)
+    assert float((y - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    for k, g in gold.items():
+        if k.startswith("act_"):
+            v = taps[k[4:]]
+            s = v[::8, ::max(1, v.shape[1] // 8), ::max(1, v.shape[2] // 4), ::max(1, v.shape[3] // 4)]
+            g = torch.from_numpy(g)[1:2]
+            assert float((s - g).abs().max()) < 1e-5 * float(g.abs().max()), k
+
+
+def test_tdn_shift_module_is_temporal_shift_at_init():
+    """With the reference's 'shift' init (tdn.py:352-358) the depthwise Conv1d is exactly TSM's temporal shift."""
+    from oracle import tdn_oracle as T
+    from oracle import tsm_oracle as O
+    c = 64
+    w = torch.zeros(c, 1, 3)
+    w[:8, 0, 2] = 1
+    w[8:16, 0, 0] = 1
+    w[16:, 0, 1] = 1
+    x = torch.randn(16, c, 5, 5, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(T.shift_module({"s.conv.weight": w}, "s", x), O.temporal_shift(x, 8, 8))

@@ -39,6 +39,8 @@ class NamedTensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
 
 
+ARCH_TSM_R50 = 0
+ARCH_TDN_R50 = 1
 MODE_BF16 = 0
 MODE_FP32_VALIDATE = 1
 
@@ -53,6 +55,8 @@ SYMBOLS = {
     "wd_engine_frame_bytes": (C.c_size_t, [_vp]),
     "wd_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp]),
     "wd_pack_nchw_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "wd_engine_clip_bytes": (C.c_size_t, [_vp]),
+    "wd_pack_tdn_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
     "wd_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _i, _vp]),
     "wd_forward_timed": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "wd_count_reps": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -21,6 +21,7 @@
 #include "wd_conv_v4.cuh"
 #include "wd_conv_2cta.cuh"
 #include "wd_stem_pool.cuh"
+#include "wd_tdn_kernels.cuh"
 
 namespace {
 
@@ -100,12 +101,17 @@ inline uint16_t f32_to_bf16_bits(float f) {  // round-to-nearest-even, as __floa
 // ---------------------------------------------------------------------------------------------------
 // Plan
 // ---------------------------------------------------------------------------------------------------
-enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_MAXPOOL = 2, OP_HEAD = 3, OP_STEMPOOL = 4 };
+enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_MAXPOOL = 2, OP_HEAD = 3, OP_STEMPOOL = 4, OP_BLEND = 5, OP_MSE = 6 };
+constexpr int kMaxBufs = 8;
+constexpr int kInDiff = -2;  // Op::in_buf: the difference tensor that follows the centre frames in a TDN input buffer
 
 struct ConvLayer {
     std::string name;      // e.g. "layer1.0.conv1"
     std::string w_key[2];  // candidate state_dict names for the conv weight
     std::string bn_prefix; // state_dict prefix of the BatchNorm
+    std::string bias_key;  // conv bias (TDN's FBResNet convolutions have bias=True), folded into the BN shift
+    bool s2d = false;      // TDN conv1_5: the 7x7/2 convolution over 12 difference channels, run as 4x4/1 over the
+                           // space-to-depth tensor [56,56,64] (wd_tdn_kernels.cuh)
     int Cin = 0, Cout = 0, k = 1, stride = 1, pad = 0;
     int Hin = 0, Win = 0, Hout = 0, Wout = 0;
     int fold = 0, relu = 0;
@@ -130,15 +136,24 @@ struct ConvLayer {
     CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
 };
 
+// TDN motion excitation + temporal Conv1d of one BottleneckShift (tdn.py:188-334, 339-376); all fp32 on device
+struct MseLayer {
+    std::string prefix;  // state_dict prefix of the block, e.g. "base_model.layer2_bak.0"
+    int C = 0, r = 0, H = 0, W = 0;
+    float *w1t = nullptr, *b1 = nullptr, *w2 = nullptr, *ws2 = nullptr, *bs2 = nullptr, *w4 = nullptr, *b4 = nullptr,
+          *w3t = nullptr, *b3 = nullptr, *wsh = nullptr;
+};
+
 struct Op {
     int kind = OP_CONV;
-    int conv = -1;           // index into convs
+    int conv = -1;           // index into convs (OP_MSE: index into mses)
     int in_buf = -1;         // -1 = external frames
     int out_buf = -1;
     int res_buf = -1;        // residual buffer or -1
     int in2_buf = -1;        // fused downsample: the block input (second A source)
     std::string name;
     int C = 0, H = 0, W = 0;  // output dims per frame
+    int Hy = 0;               // OP_BLEND: resolution of the up-sampled operand
     double macs_per_clip = 0;
 };
 
@@ -157,7 +172,9 @@ struct wd_engine {
     int sm_count = 148;
     std::vector<ConvLayer> convs;
     std::vector<Op> ops;
-    void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<MseLayer> mses;
+    int nbuf = 4;
+    void* buf[kMaxBufs] = {};
     size_t buf_elems = 0;  // elements per workspace buffer
     size_t elem_size = 2;
     float* fc_w = nullptr;  // [num_class, 2048]
@@ -317,6 +334,189 @@ int build_plan(wd_engine* e) {
     size_t mx = 0;
     for (const ConvLayer& c : e->convs)
         mx = std::max(mx, (size_t)e->desc.max_clips * 8 * c.Hout * c.Wout * c.Cout);
+    e->buf_elems = mx;
+    return WD_OK;
+}
+
+
+// Op plan for TDN ResNet-50 (workoutdetector/models/tdn.py:139-178 over FBResNet bottlenecks, tdn.py:410-520):
+//   centre frame: conv1+bn1+relu+maxpool ─┐ fuse1 = .5x + .5 up(maxpool_diff) ─ layer1_bak ─┐ fuse2 ─ layers 2-4 (with
+//   differences : conv1_5 ─ maxpool_diff ─┴─ resnext_layer1 ──────────────────────────────────┘ motion excitation) ─ head
+// Buffers 0..5 rotate, buffer 6 is the fp32 scratch of the motion-excitation kernels.
+int build_plan_tdn(wd_engine* e) {
+    const int blocks[4] = {3, 4, 6, 3};
+    const int planes[4] = {64, 128, 256, 512};
+    const bool bf = e->desc.mode == WD_MODE_BF16;
+    const int kScratch = 6;
+    e->nbuf = 7;
+    auto add_conv = [&](const std::string& name, const std::string& cv, const std::string& bn, int Cin, int Cout, int k,
+                        int stride, int Hin, int relu, bool bias) -> int {
+        ConvLayer c;
+        c.name = name;
+        c.w_key[0] = cv + ".weight";
+        if (bias) c.bias_key = cv + ".bias";
+        c.bn_prefix = bn;
+        c.Cin = Cin;
+        c.Cout = Cout;
+        c.k = k;
+        c.stride = stride;
+        c.pad = k / 2;
+        c.Hin = c.Win = Hin;
+        c.Hout = c.Wout = out_dim(Hin, k, stride, c.pad);
+        c.relu = relu;
+        e->convs.push_back(c);
+        return (int)e->convs.size() - 1;
+    };
+    auto add_conv_op = [&](int ci, int in_buf, int out_buf, int res_buf) {
+        const ConvLayer& c = e->convs[ci];
+        Op o;
+        o.kind = c.stem ? OP_STEM : OP_CONV;
+        o.conv = ci;
+        o.in_buf = in_buf;
+        o.out_buf = out_buf;
+        o.res_buf = res_buf;
+        o.name = c.name;
+        o.C = c.Cout;
+        o.H = c.Hout;
+        o.W = c.Wout;
+        o.macs_per_clip = 8.0 * c.Hout * c.Wout * (double)c.Cout * c.Cin * c.k * c.k;
+        e->ops.push_back(o);
+    };
+    auto add_simple = [&](int kind, const std::string& name, int in_buf, int out_buf, int C, int H, int Hy) {
+        Op o;
+        o.kind = kind;
+        o.in_buf = in_buf;
+        o.out_buf = out_buf;
+        o.name = name;
+        o.C = C;
+        o.H = o.W = H;
+        o.Hy = Hy;
+        e->ops.push_back(o);
+    };
+    // one bottleneck; returns the buffer holding its output
+    auto bottleneck = [&](const std::string& pre, const std::string& nm, int inplanes, int width, int stride, int H,
+                          bool mse, bool has_ds, int cur, int held) -> int {
+        int fr[3], nf = 0;
+        for (int i = 0; i < kScratch && nf < 3; ++i)
+            if (i != cur && i != held) fr[nf++] = i;
+        const int outp = width * 4;
+        const int c1 = add_conv(nm + ".conv1", pre + ".conv1", pre + ".bn1", inplanes, width, 1, 1, H, 1, true);
+        add_conv_op(c1, cur, fr[0], -1);
+        int y = fr[0], other = fr[1];
+        if (mse) {
+            MseLayer m;
+            m.prefix = pre;
+            m.C = width;
+            m.r = width / 16;
+            m.H = m.W = H;
+            e->mses.push_back(m);
+            Op o;
+            o.kind = OP_MSE;
+            o.conv = (int)e->mses.size() - 1;
+            o.in_buf = y;
+            o.out_buf = other;
+            o.name = nm + ".mse";
+            o.C = width;
+            o.H = o.W = H;
+            const double r = m.r;  // conv1, depthwise, two 3x3 branches (one at quarter size), conv3, both directions
+            o.macs_per_clip = 8.0 * H * H * (width * r + 9 * r + 2 * (9 * r * r * 1.25 + r * width));
+            e->ops.push_back(o);
+            std::swap(y, other);
+        }
+        const int c2 = add_conv(nm + ".conv2", pre + ".conv2", pre + ".bn2", width, width, 3, stride, H, 1, true);
+        add_conv_op(c2, y, other, -1);
+        std::swap(y, other);
+        const int Ho = e->convs[c2].Hout;
+        int idbuf = cur;
+        const bool fuse = has_ds && bf && (stride == 1 ? e->fuse_ds >= 1 : e->fuse_ds >= 2);
+        int cd = -1;
+        if (has_ds) {
+            cd = add_conv(nm + ".downsample", pre + ".downsample.0", pre + ".downsample.1", inplanes, outp, 1, stride, H,
+                          0, true);
+            if (fuse) {
+                e->convs[cd].fused_away = true;
+            } else {
+                add_conv_op(cd, cur, fr[2], -1);
+                idbuf = fr[2];
+            }
+        }
+        const int c3 = add_conv(nm + ".conv3", pre + ".conv3", pre + ".bn3", width, outp, 1, 1, Ho, 1, true);
+        if (fuse) {
+            e->convs[c3].fuse_ds = cd;
+            e->convs[c3].fuse_stride = stride;
+            add_conv_op(c3, y, other, -1);
+            e->ops.back().in2_buf = cur;
+            e->ops.back().macs_per_clip += 8.0 * Ho * Ho * (double)outp * inplanes;
+        } else {
+            add_conv_op(c3, y, other, idbuf);
+        }
+        return other;
+    };
+    auto layer = [&](const std::string& prefix, const std::string& name, int L, int H, bool mse, int cur, int held,
+                     int* Hout) -> int {
+        int inplanes = L == 0 ? 64 : planes[L - 1] * 4;
+        for (int b = 0; b < blocks[L]; ++b) {
+            const int stride = (L > 0 && b == 0) ? 2 : 1;
+            cur = bottleneck("base_model." + prefix + "." + std::to_string(b), name + "." + std::to_string(b), inplanes,
+                             planes[L], stride, H, mse, b == 0, cur, held);
+            if (stride == 2) H /= 2;
+            inplanes = planes[L] * 4;
+        }
+        *Hout = H;
+        return cur;
+    };
+
+    // centre frame (tdn.py:157-161)
+    int ci = add_conv("conv1", "base_model.conv1", "base_model.bn1", 3, 64, 7, 2, e->desc.height, 1, true);
+    e->convs[ci].stem = true;
+    if (bf) {
+        Op o;
+        o.kind = OP_STEMPOOL;
+        o.conv = ci;
+        o.in_buf = -1;
+        o.out_buf = 0;
+        o.name = "maxpool";
+        o.C = 64;
+        o.H = o.W = 56;
+        o.macs_per_clip = 8.0 * 112 * 112 * 64.0 * 3 * 49;
+        e->ops.push_back(o);
+    } else {
+        add_conv_op(ci, -1, 1, -1);
+        add_simple(OP_MAXPOOL, "maxpool", 1, 0, 64, 56, 0);
+    }
+    // differences (tdn.py:147-152): conv1_5 as a 4x4 convolution over the space-to-depth tensor
+    ci = add_conv("conv1_5", "base_model.conv1_5.0", "base_model.conv1_5.1", 64, 64, 4, 1, 56, 1, false);
+    e->convs[ci].s2d = true;
+    e->convs[ci].pad = 2;
+    e->convs[ci].Hout = e->convs[ci].Wout = 56;
+    add_conv_op(ci, kInDiff, 1, -1);
+    e->ops.back().macs_per_clip = 8.0 * 56 * 56 * 64.0 * 12 * 49;
+    add_simple(OP_MAXPOOL, "maxpool_diff", 1, 2, 64, 28, 0);
+    add_simple(OP_BLEND, "fuse1", 2, 0, 64, 56, 28);                       // tdn.py:162-163
+    int H = 28, Hd = 0;
+    const int xd = layer("resnext_layer1", "diff1", 0, 28, false, 2, 0, &Hd);   // tdn.py:155
+    int cur = layer("layer1_bak", "layer1", 0, 56, false, 0, xd, &H);           // tdn.py:165
+    add_simple(OP_BLEND, "fuse2", xd, cur, 256, 56, 28);                   // tdn.py:166-167
+    cur = layer("layer2_bak", "layer2", 1, 56, true, cur, -1, &H);
+    cur = layer("layer3_bak", "layer3", 2, H, true, cur, -1, &H);
+    cur = layer("layer4_bak", "layer4", 3, H, true, cur, -1, &H);
+    {
+        Op o;
+        o.kind = OP_HEAD;
+        o.in_buf = cur;
+        o.name = "head";
+        o.C = e->desc.num_class;
+        o.H = o.W = 1;
+        o.macs_per_clip = 8.0 * 2048 * e->desc.num_class;
+        e->ops.push_back(o);
+    }
+    size_t mx = 0;
+    for (const ConvLayer& c : e->convs)
+        mx = std::max(mx, (size_t)e->desc.max_clips * 8 * c.Hout * c.Wout * c.Cout);
+    for (const MseLayer& m : e->mses) {  // fp32 scratch: bott + D[2] + S2[2], in workspace elements
+        const size_t fl = (size_t)e->desc.max_clips * 8 * m.r * ((size_t)3 * m.H * m.W + 2 * (m.H / 2) * (m.W / 2));
+        mx = std::max(mx, fl * 4 / e->elem_size + 64);
+    }
     e->buf_elems = mx;
     return WD_OK;
 }
@@ -930,7 +1130,9 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
     }
     for (size_t oi = 0; oi < e->ops.size(); ++oi) {
         const Op& o = e->ops[oi];
-        const void* in = o.in_buf < 0 ? frames : e->buf[o.in_buf];
+        const void* in = o.in_buf == kInDiff
+                             ? static_cast<const uint8_t*>(frames) + (size_t)n_clips * 8 * wd_engine_frame_bytes(e)
+                             : (o.in_buf < 0 ? frames : e->buf[o.in_buf]);
         void* out = o.out_buf < 0 ? nullptr : e->buf[o.out_buf];
         const void* res = o.res_buf < 0 ? nullptr : e->buf[o.res_buf];
         if (o.kind == OP_STEMPOOL) {
@@ -950,6 +1152,7 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 a.Hout = c.Hout; a.Wout = c.Wout; a.Cout = c.Cout;
                 a.R = a.S = c.k; a.stride = c.stride; a.pad = c.pad;
                 a.fold = c.fold; a.relu = c.relu; a.stem = c.stem ? 1 : 0;
+                if (c.s2d) a.Cin = 64;
                 dim3 grid((a.M + 3) / 4, (c.Cout + 63) / 64);
                 wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
                 WD_CUDA(cudaGetLastError());
@@ -970,6 +1173,48 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                     static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n_clips, Hin, Hin, o.C);
             WD_CUDA(cudaGetLastError());
             ++e->launches;
+        } else if (o.kind == OP_BLEND) {  // x = alpha x + beta up(y); 0.5 / 0.5 for 8 segments (tdn.py:192-193)
+            const size_t total = (size_t)n_clips * o.H * o.W * 8 * (o.C / 8);
+            const unsigned grid = (unsigned)((total + 255) / 256);
+            if (f32)
+                wd::blend_up2_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(out), static_cast<const float*>(in),
+                                                                   n_clips, o.H, o.W, o.Hy, o.Hy, o.C, 0.5f, 0.5f);
+            else
+                wd::blend_up2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+                    static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(in), n_clips, o.H, o.W, o.Hy,
+                    o.Hy, o.C, 0.5f, 0.5f);
+            WD_CUDA(cudaGetLastError());
+            ++e->launches;
+        } else if (o.kind == OP_MSE) {
+            const MseLayer& ml = e->mses[o.conv];
+            const int C = ml.C, r = ml.r, H = ml.H, W = ml.W;
+            const size_t P = (size_t)n_clips * H * W, rows = P * 8;
+            const size_t P2 = (size_t)n_clips * (H / 2) * (W / 2);
+            float* bott = static_cast<float*>(e->buf[e->nbuf - 1]);
+            float* D = bott + rows * r;
+            float* S2 = D + 2 * rows * r;
+            const size_t sq_smem = (size_t)wd::kMseRows * (C + 1) * sizeof(float);
+            const unsigned g1 = (unsigned)((rows + wd::kMseRows - 1) / wd::kMseRows);
+            if (f32)
+                wd::mse_squeeze_kernel<float><<<g1, 256, sq_smem, st>>>(static_cast<const float*>(in), ml.w1t, ml.b1, bott,
+                                                                        rows, C, r);
+            else
+                wd::mse_squeeze_kernel<__nv_bfloat16><<<g1, 256, sq_smem, st>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                                ml.w1t, ml.b1, bott, rows, C, r);
+            wd::mse_diff_kernel<<<(unsigned)((rows * r + 255) / 256), 256, 0, st>>>(bott, ml.w2, D, n_clips, H, W, r);
+            wd::mse_small_kernel<<<(unsigned)((2 * P2 * 8 * r + 255) / 256), 256, 0, st>>>(D, ml.ws2, ml.bs2, S2, n_clips,
+                                                                                          H, W, r);
+            wd::MseGateArgs ga{};
+            ga.D = D; ga.S2 = S2; ga.w4 = ml.w4; ga.b4 = ml.b4; ga.w3t = ml.w3t; ga.b3 = ml.b3; ga.wsh = ml.wsh;
+            ga.clips = n_clips; ga.H = H; ga.W = W; ga.C = C; ga.r = r;
+            if (f32)
+                wd::mse_gate_shift_kernel<float><<<(unsigned)P, C, 0, st>>>(static_cast<const float*>(in),
+                                                                            static_cast<float*>(out), ga);
+            else
+                wd::mse_gate_shift_kernel<__nv_bfloat16><<<(unsigned)P, C, 0, st>>>(
+                    static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), ga);
+            WD_CUDA(cudaGetLastError());
+            e->launches += 4;
         } else {  // head
             const ConvLayer& last = e->convs.back();
             const int rows = last.Hout * last.Wout * 8;
@@ -1083,12 +1328,12 @@ const char* wd_last_error(void) { return g_err; }
 int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     if (!d || !out) return fail(WD_ERR_INVALID, "desc/out must not be NULL");
     *out = nullptr;
-    if (d->arch != WD_ARCH_TSM_R50) return fail(WD_ERR_INVALID, "unsupported arch %d", d->arch);
+    if (d->arch != WD_ARCH_TSM_R50 && d->arch != WD_ARCH_TDN_R50) return fail(WD_ERR_INVALID, "unsupported arch %d", d->arch);
     if (d->num_segments != 8) return fail(WD_ERR_INVALID, "num_segments must be 8 (got %d)", d->num_segments);
     if (d->height != 224 || d->width != 224) return fail(WD_ERR_INVALID, "input must be 224x224");
     if (d->num_class < 1 || d->num_class > wd::kMaxClasses) return fail(WD_ERR_INVALID, "bad num_class %d", d->num_class);
     if (d->max_clips < 1) return fail(WD_ERR_INVALID, "max_clips must be >= 1");
-    if (d->is_shift && (d->shift_div < 1 || 64 % d->shift_div != 0 || (64 / d->shift_div) % 8 != 0))
+    if (d->arch == WD_ARCH_TSM_R50 && d->is_shift && (d->shift_div < 1 || 64 % d->shift_div != 0 || (64 / d->shift_div) % 8 != 0))
         return fail(WD_ERR_INVALID, "shift_div=%d: fold must be a multiple of 8 channels", d->shift_div);
     if (d->mode != WD_MODE_BF16 && d->mode != WD_MODE_FP32_VALIDATE) return fail(WD_ERR_INVALID, "bad mode");
     WD_CUDA(cudaSetDevice(d->device));
@@ -1103,12 +1348,12 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
     e->fuse_ds_requested = getenv("WD_FUSE_DS") ? atoi(getenv("WD_FUSE_DS")) : 2;  // 0 off, 1 layer1.0, 2 + the stride-2 blocks
     e->fuse_ds = e->fuse_ds_requested;
-    int r = build_plan(e);
+    int r = d->arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e);
     if (r != WD_OK) {
         delete e;
         return r;
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < e->nbuf; ++i) {
         cudaError_t ce = cudaMalloc(&e->buf[i], e->buf_elems * e->elem_size);
         if (ce != cudaSuccess) {
             wd_engine_destroy(e);
@@ -1127,8 +1372,11 @@ int wd_engine_destroy(wd_engine* e) {
         if (c.w_packed) cudaFree(c.w_packed);
         if (c.bias) cudaFree(c.bias);
     }
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kMaxBufs; ++i)
         if (e->buf[i]) cudaFree(e->buf[i]);
+    for (auto& m : e->mses)
+        for (float* q : {m.w1t, m.b1, m.w2, m.ws2, m.bs2, m.w4, m.b4, m.w3t, m.b3, m.wsh})
+            if (q) cudaFree(q);
     if (e->fc_w) cudaFree(e->fc_w);
     if (e->fc_b) cudaFree(e->fc_b);
     for (int i = 0; i < 2; ++i) {
@@ -1199,18 +1447,42 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             }
             e->convs.clear();
             e->ops.clear();
+            for (auto& ml : e->mses)
+                for (float* q : {ml.w1t, ml.b1, ml.w2, ml.ws2, ml.bs2, ml.w4, ml.b4, ml.w3t, ml.b3, ml.wsh})
+                    if (q) cudaFree(q);
+            e->mses.clear();
             e->fuse_ds = want_fuse;
             e->tap_idx = -1;
-            WD_TRY(build_plan(e));
+            WD_TRY(e->desc.arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e));
         }
     }
     std::map<int, std::vector<float>> folded_w, folded_shift;
     for (ConvLayer& c : e->convs) {
-        const int64_t wn = (int64_t)c.Cout * c.Cin * c.k * c.k;
+        const int64_t wn = c.s2d ? (int64_t)c.Cout * 12 * 49 : (int64_t)c.Cout * c.Cin * c.k * c.k;
         const float* w = nullptr;
         std::string key = c.w_key[0];
         if (m.find(key) == m.end() && !c.w_key[1].empty() && m.find(c.w_key[1]) != m.end()) key = c.w_key[1];
         WD_TRY(find(key, wn, &w));
+        std::vector<float> w_s2d;
+        if (c.s2d) {
+            // [64,12,7,7] stride 2 pad 3 over the pooled differences == [64,64,4,4] stride 1 over the space-to-depth
+            // tensor (channel (py*2+px)*16 + ch, taps dr-2): input row 2(o+dr-2)+py = 2o-3+r  =>  r = 2*dr-1+py
+            w_s2d.assign((size_t)c.Cout * 64 * 16, 0.0f);
+            for (int co = 0; co < c.Cout; ++co)
+                for (int py = 0; py < 2; ++py)
+                    for (int px = 0; px < 2; ++px)
+                        for (int ch = 0; ch < 12; ++ch)
+                            for (int dr = 0; dr < 4; ++dr)
+                                for (int ds = 0; ds < 4; ++ds) {
+                                    const int r = 2 * dr - 1 + py, q = 2 * ds - 1 + px;
+                                    if (r < 0 || r > 6 || q < 0 || q > 6) continue;
+                                    w_s2d[(((size_t)co * 64 + (py * 2 + px) * 16 + ch) * 4 + dr) * 4 + ds] =
+                                        w[(((size_t)co * 12 + ch) * 7 + r) * 7 + q];
+                                }
+            w = w_s2d.data();
+        }
+        const float* cbias = nullptr;
+        if (!c.bias_key.empty()) WD_TRY(find(c.bias_key, c.Cout, &cbias));
         const float *g, *b, *mu, *var;
         WD_TRY(find(c.bn_prefix + ".weight", c.Cout, &g));
         WD_TRY(find(c.bn_prefix + ".bias", c.Cout, &b));
@@ -1221,7 +1493,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             // torch BatchNorm2d eval: y = (x - mean) / sqrt(var + eps) * weight + bias, eps = 1e-5
             const float s = g[i] / std::sqrt(var[i] + 1e-5f);
             scale[i] = s;
-            shift[i] = b[i] - mu[i] * s;
+            shift[i] = b[i] - mu[i] * s + (cbias ? cbias[i] * s : 0.0f);  // bn(conv + bias)
         }
         if (c.fused_away) {  // a 1x1 downsample that runs inside its block's conv3: keep the folded weights for it
             std::vector<float>& fw = folded_w[&c - e->convs.data()];
@@ -1260,6 +1532,8 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
         for (const Op& o : e->ops) {
             if (o.kind != OP_CONV && o.kind != OP_STEM) continue;
             ConvLayer& c = e->convs[o.conv];
+            if (o.in_buf < 0 && c.a_mode != wd::A_GATHER && c.a_mode != wd::A_STEM)
+                return fail(WD_ERR_INVALID, "%s reads the caller's buffer: gather A path only", c.name.c_str());
             const size_t rows = (size_t)e->desc.max_clips * c.Hout * c.Wout * 8;
             WD_TRY(make_omap(&c.omap, e->buf[o.out_buf], c.Cout, rows));
             if (o.res_buf >= 0) WD_TRY(make_omap(&c.rmap, e->buf[o.res_buf], c.Cout, rows));
@@ -1287,9 +1561,69 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                                  (size_t)e->desc.max_clips * c.Hin * c.Win));
         }
     }
+    auto upload = [&](float** dst, const std::vector<float>& v) -> int {
+        if (!*dst) WD_CUDA(cudaMalloc(dst, v.size() * sizeof(float)));
+        WD_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return WD_OK;
+    };
+    auto bn_fold = [&](const std::string& pfx, int n, std::vector<float>* scale, std::vector<float>* shift) -> int {
+        const float *g, *b, *mu, *var;
+        WD_TRY(find(pfx + ".weight", n, &g));
+        WD_TRY(find(pfx + ".bias", n, &b));
+        WD_TRY(find(pfx + ".running_mean", n, &mu));
+        WD_TRY(find(pfx + ".running_var", n, &var));
+        scale->resize(n);
+        shift->resize(n);
+        for (int i = 0; i < n; ++i) {
+            (*scale)[i] = g[i] / std::sqrt(var[i] + 1e-5f);
+            (*shift)[i] = b[i] - mu[i] * (*scale)[i];
+        }
+        return WD_OK;
+    };
+    for (MseLayer& ml : e->mses) {  // motion excitation + temporal Conv1d (tdn.py:188-249, 339-364), fp32
+        const int C = ml.C, r = ml.r;
+        const std::string mp = ml.prefix + ".mse";
+        const float *w1, *w2, *w3, *ws2, *ws4, *wsh;
+        WD_TRY(find(mp + ".conv1.weight", (int64_t)r * C, &w1));
+        WD_TRY(find(mp + ".conv2.weight", (int64_t)r * 9, &w2));
+        WD_TRY(find(mp + ".conv3.weight", (int64_t)C * r, &w3));
+        WD_TRY(find(mp + ".conv3_smallscale2.weight", (int64_t)r * r * 9, &ws2));
+        WD_TRY(find(mp + ".conv3_smallscale4.weight", (int64_t)r * r * 9, &ws4));
+        WD_TRY(find(ml.prefix + ".shift.conv.weight", (int64_t)C * 3, &wsh));
+        std::vector<float> sc, sh, v;
+        WD_TRY(bn_fold(mp + ".bn1", r, &sc, &sh));
+        v.resize((size_t)C * r);
+        for (int c = 0; c < C; ++c)
+            for (int j = 0; j < r; ++j) v[(size_t)c * r + j] = w1[(size_t)j * C + c] * sc[j];
+        WD_TRY(upload(&ml.w1t, v));
+        WD_TRY(upload(&ml.b1, sh));
+        v.resize((size_t)9 * r);
+        for (int j = 0; j < r; ++j)
+            for (int k = 0; k < 9; ++k) v[(size_t)k * r + j] = w2[(size_t)j * 9 + k];
+        WD_TRY(upload(&ml.w2, v));
+        for (int which = 0; which < 2; ++which) {
+            const float* wsrc = which ? ws4 : ws2;
+            WD_TRY(bn_fold(mp + (which ? ".bn3_smallscale4" : ".bn3_smallscale2"), r, &sc, &sh));
+            v.resize((size_t)9 * r * r);
+            for (int jo = 0; jo < r; ++jo)
+                for (int ji = 0; ji < r; ++ji)
+                    for (int k = 0; k < 9; ++k)
+                        v[((size_t)k * r + ji) * r + jo] = wsrc[((size_t)jo * r + ji) * 9 + k] * sc[jo];
+            WD_TRY(upload(which ? &ml.w4 : &ml.ws2, v));
+            WD_TRY(upload(which ? &ml.b4 : &ml.bs2, sh));
+        }
+        WD_TRY(bn_fold(mp + ".bn3", C, &sc, &sh));
+        v.resize((size_t)r * C);
+        for (int c = 0; c < C; ++c)
+            for (int ji = 0; ji < r; ++ji) v[(size_t)ji * C + c] = w3[(size_t)c * r + ji] * sc[c];
+        WD_TRY(upload(&ml.w3t, v));
+        WD_TRY(upload(&ml.b3, sh));
+        WD_TRY(upload(&ml.wsh, std::vector<float>(wsh, wsh + (size_t)C * 3)));
+    }
+    const bool tdn = e->desc.arch == WD_ARCH_TDN_R50;
     const float *fw, *fb;
-    WD_TRY(find("fc.weight", (int64_t)e->desc.num_class * 2048, &fw));
-    WD_TRY(find("fc.bias", e->desc.num_class, &fb));
+    WD_TRY(find(tdn ? "new_fc.weight" : "fc.weight", (int64_t)e->desc.num_class * 2048, &fw));
+    WD_TRY(find(tdn ? "new_fc.bias" : "fc.bias", e->desc.num_class, &fb));
     if (!e->fc_w) WD_CUDA(cudaMalloc(&e->fc_w, (size_t)e->desc.num_class * 2048 * sizeof(float)));
     if (!e->fc_b) WD_CUDA(cudaMalloc(&e->fc_b, (size_t)e->desc.num_class * sizeof(float)));
     WD_CUDA(cudaMemcpy(e->fc_w, fw, (size_t)e->desc.num_class * 2048 * sizeof(float), cudaMemcpyHostToDevice));
@@ -1338,6 +1672,37 @@ int wd_pack_nchw_f32(wd_engine* e, const float* x, int n_frames, void* out, void
         wd::pack_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), n_frames, pitch, pad);
     WD_CUDA(cudaGetLastError());
     ++e->launches;
+    return WD_OK;
+}
+
+size_t wd_engine_clip_bytes(const wd_engine* e) {
+    if (!e) return 0;
+    size_t b = 8 * wd_engine_frame_bytes(e);
+    if (e->desc.arch == WD_ARCH_TDN_R50) b += (size_t)56 * 56 * 8 * 64 * e->elem_size;
+    return b;
+}
+
+int wd_pack_tdn_f32(wd_engine* e, const float* x, int n_clips, void* out, void* stream) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (e->desc.arch != WD_ARCH_TDN_R50) return fail(WD_ERR_INVALID, "wd_pack_tdn_f32 needs a TDN engine");
+    if (n_clips == 0) return WD_OK;
+    if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
+    const bool bf = e->desc.mode == WD_MODE_BF16;
+    const int pitch = bf ? wd::kFramePitch : 224, pad = bf ? wd::kFramePad : 0;
+    const int S = n_clips * 8;
+    const size_t total = (size_t)S * 224 * pitch, total_d = (size_t)S * 112 * 112;
+    const unsigned grid = (unsigned)((total + 255) / 256), grid_d = (unsigned)((total_d + 255) / 256);
+    void* diff = static_cast<uint8_t*>(out) + (size_t)S * wd_engine_frame_bytes(e);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!bf) {
+        wd::tdn_pack_center_kernel<float><<<grid, 256, 0, st>>>(x, static_cast<float*>(out), S, pitch, pad);
+        wd::tdn_pack_diff_kernel<float><<<grid_d, 256, 0, st>>>(x, static_cast<float*>(diff), S);
+    } else {
+        wd::tdn_pack_center_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), S, pitch, pad);
+        wd::tdn_pack_diff_kernel<__nv_bfloat16><<<grid_d, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(diff), S);
+    }
+    WD_CUDA(cudaGetLastError());
+    e->launches += 2;
     return WD_OK;
 }
 
@@ -1463,7 +1828,7 @@ int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int
         info[5] = o.H;
         info[6] = o.W;
         info[8] = -1;
-        if (o.conv >= 0) {
+        if (o.conv >= 0 && o.kind != OP_MSE) {
             const ConvLayer& c = e->convs[o.conv];
             info[1] = c.Cin;
             info[3] = c.k;

@@ -7,7 +7,7 @@ import torch
 from . import _lib
 from ._lib import MODE_BF16, MODE_FP32_VALIDATE, ModelDesc, NamedTensor, check
 
-OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head", 4: "stem_pool"}
+OP_KINDS = {0: "stem", 1: "conv", 2: "maxpool", 3: "head", 4: "stem_pool", 5: "blend", 6: "mse"}
 A_MODES = {0: "gather", 1: "stem", 2: "tma", 3: "strip", 4: "tap", -1: "-"}
 
 
@@ -20,12 +20,13 @@ def _stream_ptr(device):
 
 
 class Engine:
-    """One TSM-R50 inference engine bound to one GPU (wd_engine_create .. wd_engine_destroy)."""
+    """One TSM-R50 (arch='tsm') or TDN-R50 (arch='tdn') inference engine bound to one GPU
+    (wd_engine_create .. wd_engine_destroy)."""
 
     def __init__(self, num_class: int, max_clips: int = 64, mode: str = "bf16", device: int = 0,
                  is_shift: bool = True, shift_div: int = 8, num_segments: int = 8,
                  use_tma_a: Optional[bool] = None, tile_n_max: Optional[int] = None,
-                 persistent: Optional[int] = None, use_strip: Optional[bool] = None):
+                 persistent: Optional[int] = None, use_strip: Optional[bool] = None, arch: str = "tsm"):
         if not torch.cuda.is_available():
             raise RuntimeError("workoutdetector_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -34,7 +35,8 @@ class Engine:
         self.max_clips = max_clips
         self.mode = {"bf16": MODE_BF16, "fp32": MODE_FP32_VALIDATE}[mode]
         self.frame_dtype = torch.bfloat16 if self.mode == MODE_BF16 else torch.float32
-        desc = ModelDesc(arch=0, num_class=num_class, num_segments=num_segments, shift_div=shift_div,
+        self.arch = arch
+        desc = ModelDesc(arch={"tsm": _lib.ARCH_TSM_R50, "tdn": _lib.ARCH_TDN_R50}[arch], num_class=num_class, num_segments=num_segments, shift_div=shift_div,
                          is_shift=int(bool(is_shift)), height=224, width=224, max_clips=max_clips, mode=self.mode,
                          device=device)
         h = C.c_void_p()
@@ -45,6 +47,7 @@ class Engine:
         # engine frames: [224, pitch, 4]; the image is columns pad .. pad+223, the rest is zero (include/wd_b200.h)
         self.frame_shape = (fh.value, fp.value, 4)
         self.frame_pad = fl.value
+        self.clip_bytes = int(self.lib.wd_engine_clip_bytes(self.h))
         if use_tma_a is not None:
             self.set_option("use_tma_a", int(use_tma_a))
         if tile_n_max is not None:
@@ -137,6 +140,19 @@ class Engine:
         check(self.lib.wd_pack_nchw_f32(self.h, _ptr(x), x.shape[0], _ptr(out), _stream_ptr(self.device)))
         return out
 
+    def pack_tdn(self, x: torch.Tensor) -> torch.Tensor:
+        """x: cuda fp32 [n,8,5,3,224,224] (or any shape that flattens to [n*8,15,224,224]; tsn.py:337-338), normalised
+        -> the TDN engine's clip buffer: n*8 centre frames, then n difference tensors [56,56,8,64] (a flat tensor of
+        n * clip_bytes bytes in the engine's element type)."""
+        assert self.arch == "tdn" and x.is_cuda and tuple(x.shape[-2:]) == (224, 224)
+        x = x.to(torch.float32).reshape(-1, 15, 224, 224).contiguous()
+        assert x.shape[0] % 8 == 0
+        n = x.shape[0] // 8
+        esz = 2 if self.mode == MODE_BF16 else 4
+        out = torch.empty((n * self.clip_bytes // esz,), dtype=self.frame_dtype, device=self.device)
+        check(self.lib.wd_pack_tdn_f32(self.h, _ptr(x), n, _ptr(out), _stream_ptr(self.device)))
+        return out
+
     def image_view(self, frames: torch.Tensor) -> torch.Tensor:
         """Engine frames -> the [n,224,224,3] image they hold (a view: no zero columns, no padding channel)."""
         return frames[:, :, self.frame_pad:self.frame_pad + 224, :3]
@@ -145,8 +161,12 @@ class Engine:
                 timed: bool = False):
         """frames [n_clips*8, *frame_shape] -> (logits [n,C] f32, probs [n,C] f32, state [n] i32[, op_ms])."""
         assert frames.is_cuda and frames.dtype == self.frame_dtype and frames.is_contiguous()
-        assert frames.shape[0] % 8 == 0 and tuple(frames.shape[1:]) == self.frame_shape
-        n = frames.shape[0] // 8
+        if self.arch == "tdn":  # the flat buffer pack_tdn() wrote
+            assert frames.dim() == 1 and (frames.numel() * frames.element_size()) % self.clip_bytes == 0
+            n = frames.numel() * frames.element_size() // self.clip_bytes
+        else:
+            assert frames.shape[0] % 8 == 0 and tuple(frames.shape[1:]) == self.frame_shape
+            n = frames.shape[0] // 8
         logits = torch.empty((n, self.num_class), dtype=torch.float32, device=self.device)
         probs = torch.empty_like(logits)
         state = torch.empty((n,), dtype=torch.int32, device=self.device)

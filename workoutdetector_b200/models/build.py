@@ -26,11 +26,12 @@ MODEL_REGISTRY = _Registry("MODEL")
 
 def build_model(cfg) -> torch.nn.Module:
     """cfg.model.model_type (case-insensitive) selects the constructor; ``**cfg.model`` is forwarded exactly as the
-    reference does (build.py:23-31). 'tsm' runs on the B200 engine; 'tdn' is not built yet."""
+    reference does (build.py:23-31). Both 'tsm' and 'tdn' run on the B200 engine."""
     model_type = cfg.model.model_type.lower()
     if model_type == "tsm":
         from .tsm import create_model as create_model_tsm
         return create_model_tsm(**cfg.model)
     if model_type == "tdn":
-        raise NotImplementedError("TDN (configs[4]) is not implemented on the B200 engine yet")
+        from .tdn import create_model as create_model_tdn
+        return create_model_tdn(**cfg.model)
     raise KeyError(f"Model '{cfg.model.model_type}' is not supported.")
