@@ -1113,6 +1113,41 @@ int launch_stem_pool(wd_engine* e, const ConvLayer& c, const void* frames, void*
     return WD_OK;
 }
 
+
+// Motion excitation + temporal Conv1d of one BottleneckShift: four launches (wd_tdn_kernels.cuh).
+template <typename T, int R>
+int launch_mse(const MseLayer& ml, const void* in, void* out, float* scratch, int n_clips, cudaStream_t st) {
+    static bool configured = false;
+    const size_t gate_smem = (size_t)(9 * R * R + wd::kGatePixels * 2 * 8 * R) * sizeof(float);
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(wd::mse_squeeze_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     512 * R * (int)sizeof(float)));
+        WD_CUDA(cudaFuncSetAttribute(wd::mse_gate_shift_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)gate_smem));
+        configured = true;
+    }
+    const int C = ml.C, H = ml.H, W = ml.W;
+    if (ml.r != R || C > 512) return fail(WD_ERR_INVALID, "motion excitation: unsupported width %d", C);
+    const size_t P = (size_t)n_clips * H * W, rows = P * 8;
+    const size_t P2 = (size_t)n_clips * (H / 2) * (W / 2);
+    float* bott = scratch;
+    float* D = bott + rows * R;
+    float* S2 = D + 2 * rows * R;
+    const unsigned T128 = wd::kMseThreads;
+    wd::mse_squeeze_kernel<T, R><<<(unsigned)((rows + T128 - 1) / T128), T128, (size_t)C * R * sizeof(float), st>>>(
+        static_cast<const T*>(in), ml.w1t, ml.b1, bott, rows, C);
+    wd::mse_diff_kernel<R><<<(unsigned)((rows + T128 - 1) / T128), T128, 0, st>>>(bott, ml.w2, D, n_clips, H, W);
+    wd::mse_small_kernel<R><<<(unsigned)((2 * P2 * 8 + T128 - 1) / T128), T128, (size_t)9 * R * R * sizeof(float), st>>>(
+        D, ml.ws2, ml.bs2, S2, n_clips, H, W);
+    wd::MseGateArgs ga{};
+    ga.D = D; ga.S2 = S2; ga.w4 = ml.w4; ga.b4 = ml.b4; ga.w3t = ml.w3t; ga.b3 = ml.b3; ga.wsh = ml.wsh;
+    ga.clips = n_clips; ga.H = H; ga.W = W; ga.C = C; ga.r = R;
+    wd::mse_gate_shift_kernel<T, R><<<(unsigned)((P + wd::kGatePixels - 1) / wd::kGatePixels), T128, gate_smem, st>>>(
+        static_cast<const T*>(in), static_cast<T*>(out), ga);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, float* probs, int32_t* state,
                 float threshold, int apply_softmax, cudaStream_t st, float* op_ms) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
@@ -1187,33 +1222,17 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
             ++e->launches;
         } else if (o.kind == OP_MSE) {
             const MseLayer& ml = e->mses[o.conv];
-            const int C = ml.C, r = ml.r, H = ml.H, W = ml.W;
-            const size_t P = (size_t)n_clips * H * W, rows = P * 8;
-            const size_t P2 = (size_t)n_clips * (H / 2) * (W / 2);
-            float* bott = static_cast<float*>(e->buf[e->nbuf - 1]);
-            float* D = bott + rows * r;
-            float* S2 = D + 2 * rows * r;
-            const size_t sq_smem = (size_t)wd::kMseRows * (C + 1) * sizeof(float);
-            const unsigned g1 = (unsigned)((rows + wd::kMseRows - 1) / wd::kMseRows);
+            float* scratch = static_cast<float*>(e->buf[e->nbuf - 1]);
+            int rc;
             if (f32)
-                wd::mse_squeeze_kernel<float><<<g1, 256, sq_smem, st>>>(static_cast<const float*>(in), ml.w1t, ml.b1, bott,
-                                                                        rows, C, r);
+                rc = ml.r == 8    ? launch_mse<float, 8>(ml, in, out, scratch, n_clips, st)
+                     : ml.r == 16 ? launch_mse<float, 16>(ml, in, out, scratch, n_clips, st)
+                                  : launch_mse<float, 32>(ml, in, out, scratch, n_clips, st);
             else
-                wd::mse_squeeze_kernel<__nv_bfloat16><<<g1, 256, sq_smem, st>>>(static_cast<const __nv_bfloat16*>(in),
-                                                                                ml.w1t, ml.b1, bott, rows, C, r);
-            wd::mse_diff_kernel<<<(unsigned)((rows * r + 255) / 256), 256, 0, st>>>(bott, ml.w2, D, n_clips, H, W, r);
-            wd::mse_small_kernel<<<(unsigned)((2 * P2 * 8 * r + 255) / 256), 256, 0, st>>>(D, ml.ws2, ml.bs2, S2, n_clips,
-                                                                                          H, W, r);
-            wd::MseGateArgs ga{};
-            ga.D = D; ga.S2 = S2; ga.w4 = ml.w4; ga.b4 = ml.b4; ga.w3t = ml.w3t; ga.b3 = ml.b3; ga.wsh = ml.wsh;
-            ga.clips = n_clips; ga.H = H; ga.W = W; ga.C = C; ga.r = r;
-            if (f32)
-                wd::mse_gate_shift_kernel<float><<<(unsigned)P, C, 0, st>>>(static_cast<const float*>(in),
-                                                                            static_cast<float*>(out), ga);
-            else
-                wd::mse_gate_shift_kernel<__nv_bfloat16><<<(unsigned)P, C, 0, st>>>(
-                    static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), ga);
-            WD_CUDA(cudaGetLastError());
+                rc = ml.r == 8    ? launch_mse<__nv_bfloat16, 8>(ml, in, out, scratch, n_clips, st)
+                     : ml.r == 16 ? launch_mse<__nv_bfloat16, 16>(ml, in, out, scratch, n_clips, st)
+                                  : launch_mse<__nv_bfloat16, 32>(ml, in, out, scratch, n_clips, st);
+            WD_TRY(rc);
             e->launches += 4;
         } else {  // head
             const ConvLayer& last = e->convs.back();
