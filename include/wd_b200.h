@@ -147,6 +147,16 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, 
                      float threshold, int apply_softmax, float* host_logits, float* host_probs,
                      int32_t* host_state);
 
+/* Streaming form of wd_infer_u8_host for callers that feed batch after batch (a video stream, a dataset pass): the
+ * call enqueues H2D copy -> preprocess -> forward -> D2H and returns; up to two batches are in flight, so the copy of
+ * batch i+1 overlaps the compute of batch i.  host_frames_hwc and the three output arrays must be PINNED host memory
+ * and stay untouched until wd_infer_host_sync (or until two later calls have been issued and synchronised, for the
+ * inputs).  Results of a call are complete after wd_infer_host_sync returns. */
+int wd_infer_u8_host_async(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, int H, int W, float in_scale,
+                           float threshold, int apply_softmax, float* host_logits, float* host_probs,
+                           int32_t* host_state);
+int wd_infer_host_sync(wd_engine* e);
+
 /* ---- introspection, tuning and test hooks (not part of the reference surface) ---- */
 int wd_engine_num_ops(const wd_engine* e);
 /* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head, 4 fused stem conv + maxpool, 5 blend with up-sampled

@@ -531,6 +531,28 @@ def test_infer_u8_host_equals_device_path(engines):
     assert torch.equal(lg_h, lg_d.cpu()) and torch.equal(pb_h, pb_d.cpu()) and torch.equal(st_h, st_d.cpu())
 
 
+def test_infer_u8_host_async_stream_of_batches(engines):
+    """Streaming form: six batches (two alternating inputs, different sizes) submitted back to back, one sync; every
+    result equals the device path's.  Exercises staging-slot reuse across calls."""
+    e = engines("bf16", "rand", max_clips=24)
+    a = synth_clips_u8(20, 13).pin_memory()
+    b = synth_clips_u8(7, 14).pin_memory()
+    want = {}
+    for k, x in (("a", a), ("b", b)):
+        want[k] = [t.cpu() for t in e.forward(e.preprocess_u8(x.cuda()))]
+    outs = []
+    for i in range(4):                     # the ring of pinned result buffers holds four sets per batch size
+        k = "ab"[i % 2]
+        outs.append((k, e.infer_u8_host_async(a if k == "a" else b)))
+    e.host_sync()
+    for k, (lg, pb, st) in outs:
+        assert torch.equal(lg, want[k][0]) and torch.equal(pb, want[k][1]) and torch.equal(st, want[k][2])
+    lg, pb, st = e.infer_u8_host(b)        # the blocking form after streaming calls
+    assert torch.equal(lg, want["b"][0]) and torch.equal(st, want["b"][2])
+    with pytest.raises(AssertionError):
+        e.infer_u8_host_async(synth_clips_u8(1, 1))   # pageable memory is refused
+
+
 def test_batch64_invariance_and_determinism(engines):
     """BASELINE cfg 2 size (64 clips): results do not depend on batch composition or on the run (no atomics, fixed
     accumulation order), and the A-operand path (TMA vs gather) and N-tile width do not change a single bit of the

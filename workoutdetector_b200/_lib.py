@@ -62,6 +62,8 @@ SYMBOLS = {
     "wd_count_reps": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "wd_scores_to_states": (_i, [_vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     "wd_infer_u8_host": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
+    "wd_infer_u8_host_async": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
+    "wd_infer_host_sync": (_i, [_vp]),
     "wd_engine_num_ops": (_i, [_vp]),
     "wd_engine_op_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "wd_engine_set_tap": (_i, [_vp, _i, _vp, C.c_int64]),

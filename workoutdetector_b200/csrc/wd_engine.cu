@@ -193,6 +193,7 @@ struct wd_engine {
     int32_t* h_state = nullptr;
     size_t h_u8_cap = 0;
     int h_chunk = 0;
+    uint64_t h_idx = 0;  // chunks submitted through the host entry points (staging slot = h_idx & 1)
 };
 
 namespace {
@@ -1764,19 +1765,23 @@ int wd_scores_to_states(const float* scores, int rows, int classes, float thresh
     return WD_OK;
 }
 
-int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int W, float in_scale, float threshold,
-                     int apply_softmax, float* host_logits, float* host_probs, int32_t* host_state) {
+static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, int H, int W, float in_scale,
+                              float threshold, int apply_softmax, float* host_logits, float* host_probs,
+                              int32_t* host_state, bool async) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
     if (!e->weights_loaded) return fail(WD_ERR_STATE, "weights not loaded");
+    if (e->desc.arch != WD_ARCH_TSM_R50) return fail(WD_ERR_INVALID, "the uint8 host entry point is the TSM path");
     if (n_clips == 0) return WD_OK;
     if (!host || !host_logits) return fail(WD_ERR_INVALID, "host_frames/host_logits must not be NULL");
+    if (n_clips > e->desc.max_clips) return fail(WD_ERR_INVALID, "n_clips=%d > max_clips=%d", n_clips, e->desc.max_clips);
     WD_CUDA(cudaSetDevice(e->desc.device));
-    // Chunk schedule: a small first chunk (its H2D copy is the only one nothing can hide) and then chunks as large
-    // as the staging buffers allow, so that the convolutions run at large-batch efficiency while the next copy
-    // streams over PCIe.  WD_HOST_CHUNK overrides the size of the later chunks.
+    // Chunk schedule.  Synchronous call: a small first chunk (its H2D copy is the only one nothing can hide) and then
+    // chunks as large as the staging buffers allow, so that the convolutions run at large-batch efficiency while the
+    // next copy streams over PCIe.  Asynchronous call: the copy hides behind the previous call's compute, so the whole
+    // batch is one chunk.  WD_HOST_CHUNK overrides the size of the later chunks.
     static const int env_chunk = getenv("WD_HOST_CHUNK") ? atoi(getenv("WD_HOST_CHUNK")) : 0;
     const int chunk = std::max(1, std::min(e->desc.max_clips, env_chunk > 0 ? env_chunk : 64));
-    const int first_chunk = std::min(chunk, 8);
+    const int first_chunk = async ? chunk : std::min(chunk, 8);
     const size_t clip_bytes = (size_t)8 * H * W * 3;
     const int C = e->desc.num_class;
     if (!e->hstream[0]) {
@@ -1791,23 +1796,28 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int 
         e->h_chunk = chunk;
     }
     if (e->h_u8_cap < (size_t)chunk * clip_bytes) {
+        WD_CUDA(cudaStreamSynchronize(e->hstream[0]));
+        WD_CUDA(cudaStreamSynchronize(e->hstream[1]));
         for (int i = 0; i < 2; ++i) {
             if (e->h_u8[i]) cudaFree(e->h_u8[i]);
             e->h_u8[i] = nullptr;
             WD_CUDA(cudaMalloc(&e->h_u8[i], (size_t)chunk * clip_bytes));
         }
         e->h_u8_cap = (size_t)chunk * clip_bytes;
+        e->h_idx = 0;
     }
-    // Copies run on hstream[slot]; compute for every chunk runs on hstream[0]-ordered stream `cs` because the
-    // workspace is shared. Slot reuse is fenced with events.
+    // Copies run on hstream[1]; compute for every chunk runs on hstream[0] because the workspace is shared.  The two
+    // staging slots alternate across chunks AND across calls (h_idx persists); reuse is fenced with events.
     cudaStream_t cs = e->hstream[0];
     cudaStream_t cp = e->hstream[1];
-    int done = 0, idx = 0;
+    int done = 0;
+    bool first = true;
     while (done < n_clips) {
-        const int nc = std::min(idx == 0 ? first_chunk : chunk, n_clips - done);
-        const int slot = idx & 1;
+        const int nc = std::min(first ? first_chunk : chunk, n_clips - done);
+        first = false;
+        const int slot = (int)(e->h_idx & 1);
         // wait until the compute that last used this slot has finished before overwriting its staging buffer
-        if (idx >= 2) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
+        if (e->h_idx >= 2) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
         WD_CUDA(cudaMemcpyAsync(e->h_u8[slot], host + (size_t)done * clip_bytes, (size_t)nc * clip_bytes,
                                 cudaMemcpyHostToDevice, cp));
         cudaEvent_t copied;
@@ -1822,15 +1832,38 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int 
                            e->h_state + done, threshold, apply_softmax, cs, nullptr));
         WD_CUDA(cudaEventRecord(e->hevent[slot], cs));
         done += nc;
-        ++idx;
+        ++e->h_idx;
     }
     WD_CUDA(cudaMemcpyAsync(host_logits, e->h_logits, (size_t)n_clips * C * sizeof(float), cudaMemcpyDeviceToHost, cs));
     if (host_probs)
         WD_CUDA(cudaMemcpyAsync(host_probs, e->h_probs, (size_t)n_clips * C * sizeof(float), cudaMemcpyDeviceToHost, cs));
     if (host_state)
         WD_CUDA(cudaMemcpyAsync(host_state, e->h_state, (size_t)n_clips * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    if (async) return WD_OK;
     WD_CUDA(cudaStreamSynchronize(cs));
     WD_CUDA(cudaStreamSynchronize(cp));
+    return WD_OK;
+}
+
+int wd_infer_u8_host(wd_engine* e, const uint8_t* host, int n_clips, int H, int W, float in_scale, float threshold,
+                     int apply_softmax, float* host_logits, float* host_probs, int32_t* host_state) {
+    return infer_u8_host_impl(e, host, n_clips, H, W, in_scale, threshold, apply_softmax, host_logits, host_probs,
+                              host_state, false);
+}
+
+int wd_infer_u8_host_async(wd_engine* e, const uint8_t* host, int n_clips, int H, int W, float in_scale,
+                           float threshold, int apply_softmax, float* host_logits, float* host_probs,
+                           int32_t* host_state) {
+    return infer_u8_host_impl(e, host, n_clips, H, W, in_scale, threshold, apply_softmax, host_logits, host_probs,
+                              host_state, true);
+}
+
+int wd_infer_host_sync(wd_engine* e) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (!e->hstream[0]) return WD_OK;
+    WD_CUDA(cudaSetDevice(e->desc.device));
+    WD_CUDA(cudaStreamSynchronize(e->hstream[0]));
+    WD_CUDA(cudaStreamSynchronize(e->hstream[1]));
     return WD_OK;
 }
 

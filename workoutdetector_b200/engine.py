@@ -57,6 +57,8 @@ class Engine:
         if use_strip is not None:
             self.set_option("use_strip", int(use_strip))
         self._tap = None
+        self._host_ring = {}
+        self._host_next = {}
 
     def close(self):
         if getattr(self, "h", None):
@@ -186,12 +188,40 @@ class Engine:
         F, H, W, _ = frames.shape
         assert F % 8 == 0
         n = F // 8
-        logits = torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True)
-        probs = torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True)
-        state = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+        logits, probs, state = self._host_out(n)
         check(self.lib.wd_infer_u8_host(self.h, _ptr(frames), n, H, W, float(in_scale), float(threshold),
                                         int(softmax), _ptr(logits), _ptr(probs), _ptr(state)))
+        return logits.clone(), probs.clone(), state.clone()   # the pinned staging tensors are reused by later calls
+
+    def _host_out(self, n: int):
+        """Pinned result buffers, a ring of four sets per batch size (pinned allocation costs ~0.1 ms per tensor, so
+        they are reused; a returned set is overwritten by the fourth later call with the same n)."""
+        ring = self._host_ring.setdefault(n, [])
+        if len(ring) < 4:
+            ring.append((torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True),
+                         torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True),
+                         torch.empty((n,), dtype=torch.int32, pin_memory=True)))
+            return ring[-1]
+        self._host_next[n] = (self._host_next.get(n, 0) + 1) % 4
+        return ring[self._host_next[n]]
+
+    def infer_u8_host_async(self, frames: torch.Tensor, in_scale: float = 1.0 / 255.0, threshold: float = 0.5,
+                            softmax: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Streaming form: PINNED host uint8 [n_clips*8,H,W,3] is enqueued (H2D -> preprocess -> forward -> D2H) and
+        the call returns pinned (logits, probs, state) that are valid after ``host_sync()``.  Two batches are in
+        flight, so the copy of the next batch overlaps the compute of this one; ``frames`` must stay untouched until
+        the sync."""
+        assert not frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and frames.is_pinned()
+        F, H, W, _ = frames.shape
+        assert F % 8 == 0
+        n = F // 8
+        logits, probs, state = self._host_out(n)
+        check(self.lib.wd_infer_u8_host_async(self.h, _ptr(frames), n, H, W, float(in_scale), float(threshold),
+                                              int(softmax), _ptr(logits), _ptr(probs), _ptr(state)))
         return logits, probs, state
+
+    def host_sync(self):
+        check(self.lib.wd_infer_host_sync(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.wd_engine_launch_count(self.h))
