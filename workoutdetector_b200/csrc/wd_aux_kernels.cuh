@@ -419,6 +419,116 @@ head_kernel(const T* __restrict__ feat,  // [clips, rows_per_clip, C]
     }
 }
 
+// Split form of head_kernel for the bf16 product path: kHeadParts CTAs per clip each reduce a quarter of the clip's rows
+// (256 CTAs instead of 64 keep all SMs loading), write their partial column sums to scratch, and the CTA that arrives
+// last (atomic ticket per clip) adds the partials in a FIXED order — results stay run-to-run bit-exact — and runs the
+// FC / softmax / arg-max phases.  The ticket is reset by that CTA for the next launch.
+constexpr int kHeadParts = 4;
+constexpr int kHeadSplitThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kHeadSplitThreads)
+head_split_kernel(const T* __restrict__ feat, const float* __restrict__ wfc, const float* __restrict__ bfc,
+                  int rows_per_clip, int C, int classes, float threshold, int apply_softmax, float* __restrict__ partial,
+                  unsigned int* __restrict__ ticket, float* __restrict__ logits, float* __restrict__ probs,
+                  int32_t* __restrict__ state) {
+    pdl_grid_dependency_wait();
+    pdl_launch_dependents();
+    extern __shared__ float sm[];  // C feature means, then `classes` logits
+    __shared__ bool is_last;
+    const int n = blockIdx.x, part = blockIdx.y;
+    const T* base = feat + (size_t)n * rows_per_clip * C;
+    const int rpp = (rows_per_clip + kHeadParts - 1) / kHeadParts;
+    const int r0 = part * rpp, r1 = min(r0 + rpp, rows_per_clip);
+    float* mine = partial + ((size_t)n * kHeadParts + part) * C;
+    for (int c8 = threadIdx.x; c8 < C / 8; c8 += kHeadSplitThreads) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // seven independent 16-byte loads are issued before the first one is consumed: a row-at-a-time loop runs at one
+        // L2 round trip per row (98 x ~0.7 us), which is what bounded the single-CTA-per-clip head_kernel
+        for (int r = r0; r < r1; r += 7) {
+            float v[7][8];
+#pragma unroll
+            for (int i = 0; i < 7; ++i)   // unconditional (row index clamped): a guarded load would be waited on in place
+                load8(base + (size_t)min(r + i, r1 - 1) * C + c8 * 8, v[i]);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float keep = (r + i < r1) ? 1.0f : 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = fmaf(v[i][q], keep, acc[q]);
+            }
+        }
+        store8(mine + c8 * 8, acc);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket + n, 1u) == (unsigned)(kHeadParts - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float* sfeat = sm;
+    float* slog = sm + C;
+    const float inv = 1.0f / (float)rows_per_clip;
+    const float* pp = partial + (size_t)n * kHeadParts * C;
+    for (int c = threadIdx.x; c < C; c += kHeadSplitThreads) {
+        float s = __ldcg(pp + c);
+#pragma unroll
+        for (int q = 1; q < kHeadParts; ++q) s += __ldcg(pp + (size_t)q * C + c);
+        sfeat[c] = s * inv;
+    }
+    if (threadIdx.x == 0) ticket[n] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < classes; k += kHeadSplitThreads / 32) {
+        const float4* w4 = reinterpret_cast<const float4*>(wfc + (size_t)k * C);
+        const float4* f4 = reinterpret_cast<const float4*>(sfeat);
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int c4 = lane; c4 < C / 4; c4 += 32) {  // 128-bit weight loads, eight in flight per lane
+            const float4 w = __ldg(w4 + c4), f = f4[c4];
+            acc += (w.x * f.x + w.y * f.y) + (w.z * f.z + w.w * f.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const float v = acc + __ldg(bfc + k);
+            slog[k] = v;
+            logits[(size_t)n * classes + k] = v;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -INFINITY;
+        int arg = 0x7fffffff;
+        for (int k = lane; k < classes; k += 32) {
+            const float v = slog[k];
+            if (v > mx) {
+                mx = v;
+                arg = k;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (omx > mx || (omx == mx && oarg < arg)) {
+                mx = omx;
+                arg = oarg;
+            }
+        }
+        float sum = 0.0f;
+        for (int k = lane; k < classes; k += 32) sum += expf(slog[k] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float rs = 1.0f / sum;
+        if (probs)
+            for (int k = lane; k < classes; k += 32) probs[(size_t)n * classes + k] = expf(slog[k] - mx) * rs;
+        if (state && lane == 0) {
+            const float top = apply_softmax ? rs : mx;
+            state[n] = (top >= threshold) ? arg : -1;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Scores -> states for score arrays that already exist (the JSON route of utils/eval.py:153-164): one warp per
 // window row; softmax (optional), first-max arg-max, threshold. Same arithmetic as phase 3 of head_kernel.

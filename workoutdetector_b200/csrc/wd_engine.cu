@@ -179,6 +179,8 @@ struct wd_engine {
     size_t elem_size = 2;
     float* fc_w = nullptr;  // [num_class, 2048]
     float* fc_b = nullptr;
+    float* head_partial = nullptr;      // [max_clips, kHeadParts, 2048] partial column sums of the split head
+    unsigned int* head_ticket = nullptr;  // [max_clips] arrival counters (zero between launches)
     int tap_idx = -1;
     float* tap_dst = nullptr;
     int64_t tap_cap = 0;
@@ -544,6 +546,23 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_grid(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+int g_head_split = getenv("WD_HEAD_SPLIT") ? atoi(getenv("WD_HEAD_SPLIT")) : 1;  // 4 CTAs per clip in the head
+
 template <int BN, int STAGES, int AMODE>
 int launch_conv_t(const CUtensorMap& wmap, const CUtensorMap& amap, const wd::ConvArgs& a, cudaStream_t st) {
     using L = wd::ConvSmem<BN, STAGES>;
@@ -1019,6 +1038,8 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
         c.a_mode = wd::A_TMA;
     else if (use_strip && c.k == 3 && c.stride == 1 && c.Wout % wd::kStripPixels == 0 && c.Wout >= wd::kStripPixels)
         c.a_mode = wd::A_STRIP;
+    else if (c.s2d && use_tma_a && use_strip && v4 && g_tap)
+        c.a_mode = wd::A_TAP;  // TDN conv1_5 (4x4 taps over the space-to-depth differences): 14-pixel tap boxes
     else if (use_strip && v4 && g_tap && c.fold == 0 && (c.k == 3 || c.stride == 2) &&
              (c.Wout % wd::kStripPixels == 0 || (c.Wout == 7 && (g_tap >= 2 || (g_2cta >= 3 && c.tile_n == 256)))))
         c.a_mode = wd::A_TAP;  // stride-2 convolutions: one TMA box per (tap, channel block).  7-pixel rows (two boxes per
@@ -1192,6 +1213,11 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 dim3 grid((a.M + 3) / 4, (c.Cout + 63) / 64);
                 wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
                 WD_CUDA(cudaGetLastError());
+            } else if (o.in_buf == kInDiff && c.a_mode == wd::A_TAP) {
+                ConvLayer cc = c;  // tap boxes over the caller's difference tensor: its address is known only now
+                WD_TRY(make_amap_tap(&cc.amap, in, c.Cin, c.Win, c.Hin, (size_t)n_clips, 1, wd::kStripPixels));
+                wd::ConvArgs a = conv_args(cc, in, out, res, n_clips);
+                WD_TRY(launch_any(cc, a, e->persistent, e->sm_count, st));
             } else {
                 wd::ConvArgs a = conv_args(c, in, out, res, n_clips);
                 WD_TRY(launch_any(c, a, e->persistent, e->sm_count, st));
@@ -1244,7 +1270,13 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 wd::head_kernel<float><<<n_clips, wd::kHeadThreads, smem, st>>>(
                     static_cast<const float*>(in), e->fc_w, e->fc_b, rows, C, e->desc.num_class, threshold,
                     apply_softmax, logits, probs, state);
-            else
+            else if (g_head_split) {
+                const size_t smem2 = (size_t)(C + e->desc.num_class) * sizeof(float);
+                WD_CUDA(launch_pdl_grid(wd::head_split_kernel<__nv_bfloat16>, dim3((unsigned)n_clips, wd::kHeadParts),
+                                        (unsigned)wd::kHeadSplitThreads, smem2, st, static_cast<const __nv_bfloat16*>(in),
+                                        (const float*)e->fc_w, (const float*)e->fc_b, rows, C, (int)e->desc.num_class,
+                                        threshold, apply_softmax, e->head_partial, e->head_ticket, logits, probs, state));
+            } else
                 WD_CUDA(launch_pdl(wd::head_kernel<__nv_bfloat16>, (unsigned)n_clips, (unsigned)wd::kHeadThreads, smem, st,
                                    static_cast<const __nv_bfloat16*>(in), (const float*)e->fc_w, (const float*)e->fc_b, rows,
                                    C, (int)e->desc.num_class, threshold, apply_softmax, logits, probs, state));
@@ -1397,6 +1429,8 @@ int wd_engine_destroy(wd_engine* e) {
     for (auto& m : e->mses)
         for (float* q : {m.w1t, m.b1, m.w2, m.ws2, m.bs2, m.w4, m.b4, m.w3t, m.b3, m.wsh})
             if (q) cudaFree(q);
+    if (e->head_partial) cudaFree(e->head_partial);
+    if (e->head_ticket) cudaFree(e->head_ticket);
     if (e->fc_w) cudaFree(e->fc_w);
     if (e->fc_b) cudaFree(e->fc_b);
     for (int i = 0; i < 2; ++i) {
@@ -1552,14 +1586,18 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
         for (const Op& o : e->ops) {
             if (o.kind != OP_CONV && o.kind != OP_STEM) continue;
             ConvLayer& c = e->convs[o.conv];
-            if (o.in_buf < 0 && c.a_mode != wd::A_GATHER && c.a_mode != wd::A_STEM)
-                return fail(WD_ERR_INVALID, "%s reads the caller's buffer: gather A path only", c.name.c_str());
+            if (o.in_buf < 0 && c.a_mode != wd::A_GATHER && c.a_mode != wd::A_STEM && c.a_mode != wd::A_TAP)
+                return fail(WD_ERR_INVALID, "%s reads the caller's buffer: gather / tap A path only", c.name.c_str());
             const size_t rows = (size_t)e->desc.max_clips * c.Hout * c.Wout * 8;
             WD_TRY(make_omap(&c.omap, e->buf[o.out_buf], c.Cout, rows));
             if (o.res_buf >= 0) WD_TRY(make_omap(&c.rmap, e->buf[o.res_buf], c.Cout, rows));
             if (c.a_mode == wd::A_STRIP) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
                 WD_TRY(make_amap5(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
+            }
+            if (c.a_mode == wd::A_TAP && o.in_buf < 0) {  // the A map over the caller's buffer is encoded per call
+                WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
+                continue;
             }
             if (c.a_mode == wd::A_TAP) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
@@ -1644,6 +1682,11 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     const float *fw, *fb;
     WD_TRY(find(tdn ? "new_fc.weight" : "fc.weight", (int64_t)e->desc.num_class * 2048, &fw));
     WD_TRY(find(tdn ? "new_fc.bias" : "fc.bias", e->desc.num_class, &fb));
+    if (!e->head_partial) {
+        WD_CUDA(cudaMalloc(&e->head_partial, (size_t)e->desc.max_clips * wd::kHeadParts * 2048 * sizeof(float)));
+        WD_CUDA(cudaMalloc(&e->head_ticket, (size_t)e->desc.max_clips * sizeof(unsigned int)));
+        WD_CUDA(cudaMemset(e->head_ticket, 0, (size_t)e->desc.max_clips * sizeof(unsigned int)));
+    }
     if (!e->fc_w) WD_CUDA(cudaMalloc(&e->fc_w, (size_t)e->desc.num_class * 2048 * sizeof(float)));
     if (!e->fc_b) WD_CUDA(cudaMalloc(&e->fc_b, (size_t)e->desc.num_class * sizeof(float)));
     WD_CUDA(cudaMemcpy(e->fc_w, fw, (size_t)e->desc.num_class * 2048 * sizeof(float), cudaMemcpyHostToDevice));
