@@ -417,7 +417,8 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();  // the peer may still be arriving on / reading from this CTA's shared memory and TMEM
-    if (warp == 5) tmem_dealloc_2cta(tmem_base, 512);
+    if (warp == 5) tmem_dealloc_2cta(tmem_base, 2 * BN);  // must equal the allocation (a 512-column dealloc of a
+                                                          // 256-column allocation faults: the BN = 128 bug of round 1)
 }
 
 

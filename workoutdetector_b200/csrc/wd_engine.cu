@@ -795,8 +795,11 @@ int g_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 4;  // cta_group::2 k
 
 // CTA-pair kernel (wd_conv_2cta.cuh): 1x1 stride-1, no residual, 256-wide Cout tiles, K >= 256.
 bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
-    // 256-wide tiles only: the BN = 128 instantiation of conv_2cta_kernel faults on the device (not a barrier
-    // time-out; cause not found in round 1) and is not dispatched.
+    // 128-wide tiles: only the stride-2 3x3 of layer 2 (tap boxes, K = 1152) — the 1x1 convolutions with Cout = 128 sit
+    // on the HBM roofline and gain nothing from sharing W
+    if (g_2cta >= 3 && c.tile_n == 128 && c.Cout % 128 == 0 && c.a_mode == wd::A_TAP && c.kb_split == 0 &&
+        a.residual == nullptr && a.kblocks >= 8 && a.Wout != 7)
+        return true;
     if (!g_2cta || c.tile_n != 256 || c.Cout % 256 != 0 || (c.kb_split > 0 && c.a_mode != wd::A_TAP)) return false;
     if (a.residual != nullptr)  // conv3 of layers 3-4 (K >= 256): pair kernel with the in-place residual epilogue
         return g_2cta >= 4 && c.a_mode == wd::A_TMA && a.kblocks >= 4 && a.fold == 0;
@@ -851,6 +854,7 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
 }
 
 int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    if (c.tile_n == 128) return launch_2cta_t<128, true, false>(c, a, sm_count, st);
     if (a.residual != nullptr) return launch_2cta_t<256, false, true>(c, a, sm_count, st);
     return c.a_mode == wd::A_TAP ? launch_2cta_t<256, true, false>(c, a, sm_count, st)
                                  : launch_2cta_t<256, false, false>(c, a, sm_count, st);
