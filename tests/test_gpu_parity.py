@@ -573,6 +573,69 @@ def test_batch64_invariance_and_determinism(engines):
     assert len(set(a[2].tolist())) >= 1 and a[0].isfinite().all()
 
 
+def test_cfg3_32_videos_of_1080_frames(weights, count_oracle_c):
+    """BASELINE configs[2] at full size: 32 videos x 1080 frames x 224x224x3 uint8 -> even-frame windows (135 per video,
+    the last one 4 real + 4 zero frames) -> 4320 clips -> states [32,135] -> batched counter.  Checked through
+    size-independent properties: window table shape, state == threshold/arg-max rule on the returned scores, chunking
+    invariance and run-to-run determinism (bit-exact), counter == the C oracle on the same states (bit-exact)."""
+    import ctypes as C
+    from workoutdetector_b200.models import create_model
+    from workoutdetector_b200.utils.inference_count import pred_to_count_batch, score_windows, window_index_table
+    m = create_model(12, device="cuda")
+    sd = dict(weights["rand"])
+    g = torch.Generator().manual_seed(5)
+    sd["fc.weight"] = torch.randn(12, 2048, generator=g) * 1.5      # a steep head: states follow the motion phase
+    m.load_state_dict(sd)
+    V, F_ = 32, 1080
+    table = window_index_table(F_)
+    assert table.shape == (135, 8) and table[-1].tolist() == [1072, 1074, 1076, 1078, -1, -1, -1, -1]
+    assert table[0].tolist() == list(range(0, 16, 2)) and int(table[1, 0]) == 8
+    yy, xx = torch.meshgrid(torch.arange(224, device="cuda"), torch.arange(224, device="cuda"), indexing="ij")
+    states = torch.empty((V, 135), dtype=torch.int32, device="cuda")
+
+    def video(v):
+        gg = torch.Generator(device="cuda").manual_seed(v)
+        base = torch.rand(1, 224, 224, 3, device="cuda", generator=gg)
+        t = torch.arange(F_, device="cuda").view(-1, 1, 1, 1).float()
+        period = 40 + 5 * (v % 7)
+        phase = torch.sin(2 * torch.pi * t / period)                                  # the "repetition"
+        blob = torch.exp(-(((yy - 112 - 60 * phase[:, :, :, 0]) ** 2 + (xx - 112) ** 2) / 1800.0)).unsqueeze(-1)
+        return ((0.35 * base + 0.65 * blob) * 255).clamp(0, 255).to(torch.uint8)      # [1080,224,224,3]
+
+    # centre and steepen the head on video 0 so that the arg-max follows the motion phase instead of one fixed class
+    lg0, _, _ = score_windows(m, video(0), table)
+    mu, sig = lg0.mean(0).cpu(), float(lg0.std(0).max())
+    scale = 6.0 / max(sig, 1e-6)
+    sd["fc.bias"] = -scale * (mu - sd["fc.bias"])
+    sd["fc.weight"] = scale * sd["fc.weight"]
+    m.load_state_dict(sd)
+    for v in range(V):
+        vid = video(v)
+        lg, pb, st = score_windows(m, vid, table)
+        assert lg.shape == (135, 12)
+        top, arg = pb.max(dim=1)
+        assert torch.equal(st, torch.where(top >= 0.5, arg.int(), torch.full_like(st, -1)))
+        if v % 8 == 0:                                                                # chunking invariance + determinism
+            parts = [score_windows(m, vid, table[a:b]) for a, b in ((0, 45), (45, 46), (46, 135))]
+            lg2, st2 = torch.cat([q[0] for q in parts]), torch.cat([q[2] for q in parts])
+            lg3, _, _ = score_windows(m, vid, table)
+            assert torch.equal(lg, lg2) and torch.equal(st, st2) and torch.equal(lg, lg3)
+        states[v] = st
+    counts, reps, rl = pred_to_count_batch(states, None, 8)
+    hs = states.cpu().contiguous()
+    oc = torch.zeros(V, dtype=torch.int32)
+    orp = torch.zeros((V, 136), dtype=torch.int32)
+    orl = torch.zeros(V, dtype=torch.int32)
+    count_oracle_c.oracle_count_reps(C.c_void_p(hs.data_ptr()), None, V, 135, 8, C.c_void_p(oc.data_ptr()),
+                                     C.c_void_p(orp.data_ptr()), 136, C.c_void_p(orl.data_ptr()))
+    assert torch.equal(counts.cpu(), oc) and torch.equal(rl.cpu(), orl)
+    for v in range(V):
+        assert reps[v, :int(rl[v])].cpu().tolist() == orp[v, :int(orl[v])].tolist()
+        assert (int(oc[v]), orp[v, :int(orl[v])].tolist()) == CO.pred_to_count(hs[v].tolist(), 8)
+    assert len(set(hs.flatten().tolist())) >= 3          # the states really vary
+    print("cfg3: counts", oc.tolist())
+
+
 def test_abi_error_paths(weights):
     """Error behaviour at the C ABI: negative status + message, never a crash."""
     import ctypes as C
@@ -599,3 +662,38 @@ def test_abi_error_paths(weights):
     e.forward(fr)
     assert e.launch_count() == len(e.ops())     # fused stem+maxpool, 48 convs (downsamples folded into conv3), head: all this library's kernels
     e.close()
+
+
+def test_engine_session_ort_surface(weights, tsm_gold):
+    """serving.EngineSession: the onnxruntime call surface of the reference's callers (inference_count.py:265-276,
+    app/inference.py:54-78) on the engine; 11-class softmax output for the action-recognition demo (configs[4])."""
+    from workoutdetector_b200.models import create_model
+    from workoutdetector_b200.serving import EngineSession
+    from workoutdetector_b200.utils.inference_count import inference_video
+    m = create_model(12, device="cuda")
+    m.load_state_dict(weights["rand"])
+    sess = EngineSession(m)
+    x = torch.randn(16, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    name = sess.get_inputs()[0].name
+    out = sess.run(None, {name: x.view(2, 8, 3, 224, 224).numpy()})[0]
+    ref = tsm_gold["logits_rand_noise"]
+    assert out.shape == (2, 12) and out.dtype == np.float32
+    assert float(np.abs(torch.softmax(torch.from_numpy(out), 1).numpy() - torch.softmax(torch.from_numpy(ref), 1).numpy()).max()) < TOL_BF16
+    with pytest.raises(KeyError):
+        sess.run(None, {"wrong": x.numpy()})
+    # inference_video's ORT branch drives it like an onnxruntime session
+    u8 = synth_clips_u8(1, 3)
+    from workoutdetector_b200.datasets import build_test_transform
+    pred = inference_video(sess, u8, transform=build_test_transform(person_crop=False))
+    direct = inference_video(m, u8)
+    assert [p[0] for p in pred] == [p[0] for p in direct]
+    assert max(abs(a[1] - b[1]) for a, b in zip(pred, direct)) < 5e-2
+    # 11-class probabilities
+    sd11 = O.randomize_bn_and_fc(O.reference_init_state_dict(11, 0), 1)
+    m11 = create_model(11, device="cuda")
+    m11.load_state_dict(sd11)
+    p11 = EngineSession(m11, softmax=True).run(None, {"input": x.view(2, 8, 3, 224, 224).numpy()})[0]
+    with torch.no_grad():
+        want = torch.softmax(O.tsm_forward(sd11, x), 1).numpy()
+    assert p11.shape == (2, 11) and abs(float(p11.sum()) - 2.0) < 1e-4
+    assert float(np.abs(p11 - want).max()) < TOL_BF16
