@@ -443,6 +443,7 @@ struct Conv2CtaStripArgs {
     int num_strips;    // clips * H * (W / 14)
     int tiles_w;       // W / 14
     int w_stages;      // W ring depth
+    int w_resident;    // w_stages == 9 * cin_blocks: every tap's W half is loaded once and stays (layer 1, Cin = 64)
     int off_w, off_out, off_bar;  // byte offsets (A ring of two kStripStage stages at 0)
 };
 
@@ -461,12 +462,12 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
     uint64_t* a_full = bars;               // [2]  (leader's)
     uint64_t* a_empty = bars + 2;          // [2]
-    uint64_t* w_full = bars + 8;           // [8]  (leader's)
-    uint64_t* w_empty = bars + 16;         // [8]
-    uint64_t* tmem_full_bar = bars + 24;   // [2]
-    uint64_t* tmem_empty_bar = bars + 26;  // [2]  (leader's)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 28);
-    float* sBias = reinterpret_cast<float*>(bars + 32);  // BN floats
+    uint64_t* w_full = bars + 8;           // [16]  (leader's)
+    uint64_t* w_empty = bars + 24;         // [16]
+    uint64_t* tmem_full_bar = bars + 40;   // [2]
+    uint64_t* tmem_empty_bar = bars + 42;  // [2]  (leader's)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 44);
+    float* sBias = reinterpret_cast<float*>(bars + 48);  // BN floats
 
     pdl_launch_dependents();
     const int tid = threadIdx.x;
@@ -487,7 +488,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                 mbar_init(&a_full[s], 6);
                 mbar_init(&a_empty[s], 1);
             }
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < 16; ++s) {
                 mbar_init(&w_full[s], 2);
                 mbar_init(&w_empty[s], 1);
             }
@@ -589,6 +590,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         // ============================== W producer: this CTA's half of every tap ==============================
         uint32_t it = 0;
         for (int tile = pair; tile < a.num_tiles; tile += npairs) {
+            if (a.w_resident && tile != pair) break;  // all taps were loaded with the first tile and stay
             for (int cb = 0; cb < a.cin_blocks; ++cb) {
                 for (int tap = 0; tap < 9; ++tap, ++it) {
                     const int slot = it % a.w_stages;
@@ -625,8 +627,10 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap, ++itw) {
                         const int wslot = itw % a.w_stages;
-                        mbar_wait(&w_full[wslot], (itw / a.w_stages) & 1);
-                        tc_fence_after_sync();
+                        if (!a.w_resident || tile_iter == 0) {
+                            mbar_wait(&w_full[wslot], (itw / a.w_stages) & 1);
+                            tc_fence_after_sync();
+                        }
                         const uint64_t adesc =
                             umma_desc_from_lo(a_lo + (uint32_t)((tap / 3) * (16384 >> 4) + (tap % 3) * (1024 >> 4)));
                         const uint64_t bdesc = umma_desc_from_lo(sW_lo + ((uint32_t)(wslot * kWHalf) >> 4));
@@ -636,7 +640,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
 #pragma unroll
                             for (int k = 1; k < kTileK / 16; ++k)
                                 umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
-                            umma_commit_2cta(&w_empty[wslot]);
+                            if (!a.w_resident) umma_commit_2cta(&w_empty[wslot]);
                             if (tap == 8) {
                                 umma_commit_2cta(&a_empty[aslot]);
                                 if (cb == a.cin_blocks - 1) umma_commit_2cta(&tmem_full_bar[acc]);

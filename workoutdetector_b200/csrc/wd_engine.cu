@@ -882,6 +882,11 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     const int whalf = (BN / 2) * 128;
     const int fixed = 2 * wd::kStripStage + 8 * wd::kEpiSlab + 2048 + 1024;
     p.w_stages = std::min(8, (232448 - fixed) / whalf);
+    p.w_resident = 0;
+    if (9 * a.cin_blocks <= 16 && 9 * a.cin_blocks * whalf <= 232448 - fixed) {  // layer 1 (Cin = 64): W stays in smem
+        p.w_stages = 9 * a.cin_blocks;
+        p.w_resident = 1;
+    }
     p.off_w = 2 * wd::kStripStage;
     p.off_out = p.off_w + p.w_stages * whalf;
     p.off_bar = p.off_out + 8 * wd::kEpiSlab;
@@ -908,6 +913,8 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
 
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
     if (eligible_2cta(c, a)) return launch_2cta(c, a, sm_count, st);
+    if (g_2cta >= 5 && c.a_mode == wd::A_STRIP && a.residual == nullptr && c.tile_n == 64)
+        return launch_2cta_strip<64>(c, a, sm_count, st);  // narrow tiles on a CTA pair: 256 x 64 per instruction
     if (g_2cta >= 2 && c.a_mode == wd::A_STRIP && a.residual == nullptr && a.cin_blocks * 9 * c.tile_n * 128 > 73728) {
         if (c.tile_n == 256) return launch_2cta_strip<256>(c, a, sm_count, st);
         if (c.tile_n == 128) return launch_2cta_strip<128>(c, a, sm_count, st);
@@ -1062,7 +1069,7 @@ int upload_conv(ConvLayer& c, int mode, int tile_n_max, int use_tma_a, const flo
     }
     const uint32_t box[2] = {64, (uint32_t)c.tile_n};
     WD_TRY(make_tmap_bf16(&c.wmap, c.w_packed, 2, dims, strides, box));
-    if (c.tile_n >= 128) {
+    if (c.tile_n >= 64) {
         const uint32_t box_half[2] = {64, (uint32_t)c.tile_n / 2};
         WD_TRY(make_tmap_bf16(&c.wmap_half, c.w_packed, 2, dims, strides, box_half));
     }
@@ -1458,7 +1465,7 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
         e->persistent = value;
     } else if (!strcmp(key, "use_2cta")) {
-        if (value < 0 || value > 4) return fail(WD_ERR_INVALID, "use_2cta must be 0..4");
+        if (value < 0 || value > 5) return fail(WD_ERR_INVALID, "use_2cta must be 0..5");
         g_2cta = value;
     } else if (!strcmp(key, "pdl")) {
         g_pdl = value ? 1 : 0;
