@@ -1154,7 +1154,7 @@ int launch_mse(const MseLayer& ml, const void* in, void* out, float* scratch, in
     const size_t gate_smem = (size_t)(9 * R * R + wd::kGatePixels * 2 * 8 * R) * sizeof(float);
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(wd::mse_squeeze_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     512 * R * (int)sizeof(float)));
+                                     512 * R * (int)sizeof(float) + wd::kMseThreads * wd::kSqRowBytes<T>));
         WD_CUDA(cudaFuncSetAttribute(wd::mse_gate_shift_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)gate_smem));
         configured = true;
@@ -1167,7 +1167,8 @@ int launch_mse(const MseLayer& ml, const void* in, void* out, float* scratch, in
     float* D = bott + rows * R;
     float* S2 = D + 2 * rows * R;
     const unsigned T128 = wd::kMseThreads;
-    wd::mse_squeeze_kernel<T, R><<<(unsigned)((rows + T128 - 1) / T128), T128, (size_t)C * R * sizeof(float), st>>>(
+    wd::mse_squeeze_kernel<T, R><<<(unsigned)((rows + T128 - 1) / T128), T128,
+                                   (size_t)C * R * sizeof(float) + (size_t)T128 * wd::kSqRowBytes<T>, st>>>(
         static_cast<const T*>(in), ml.w1t, ml.b1, bott, rows, C);
     wd::mse_diff_kernel<R><<<(unsigned)((rows + T128 - 1) / T128), T128, 0, st>>>(bott, ml.w2, D, n_clips, H, W);
     wd::mse_small_kernel<R><<<(unsigned)((2 * P2 * 8 + T128 - 1) / T128), T128, (size_t)9 * R * R * sizeof(float), st>>>(

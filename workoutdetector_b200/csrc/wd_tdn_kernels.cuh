@@ -90,6 +90,51 @@ __device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
 }
 __device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
+__device__ __forceinline__ float tanh_approx(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+// N = 2 or 4 adjacent channels <-> floats, one vector access
+template <int N>
+__device__ __forceinline__ void loadN(const __nv_bfloat16* p, float (&f)[N]) {
+    if constexpr (N == 2) {
+        load2(p, f[0], f[1]);
+    } else {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        f[0] = __uint_as_float(v.x << 16);
+        f[1] = __uint_as_float(v.x & 0xFFFF0000u);
+        f[2] = __uint_as_float(v.y << 16);
+        f[3] = __uint_as_float(v.y & 0xFFFF0000u);
+    }
+}
+template <int N>
+__device__ __forceinline__ void loadN(const float* p, float (&f)[N]) {
+    if constexpr (N == 2) {
+        load2(p, f[0], f[1]);
+    } else {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+}
+template <int N>
+__device__ __forceinline__ void storeN(__nv_bfloat16* p, const float (&f)[N]) {
+    if constexpr (N == 2) {
+        store2(p, f[0], f[1]);
+    } else {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+}
+template <int N>
+__device__ __forceinline__ void storeN(float* p, const float (&f)[N]) {
+    if constexpr (N == 2) {
+        store2(p, f[0], f[1]);
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+}
+
 // x[clip, H, W, t, C] = alpha * x + beta * y[clip, h*Hy/H, w*Wy/W, t, C]  (F.interpolate, mode='nearest'), in place.
 template <typename T>
 __global__ void blend_up2_kernel(T* __restrict__ x, const T* __restrict__ y, int clips, int H, int W, int Hy, int Wy,
@@ -125,37 +170,65 @@ __global__ void blend_up2_kernel(T* __restrict__ x, const T* __restrict__ y, int
 constexpr int kMseThreads = 128;
 constexpr int kGatePixels = 8;  // pixels per block of mse_gate_shift_kernel
 
-// bott = bn1(conv1(x)):  w1t [C, R] (BN scale folded), b1 [R].  One thread per row (pixel, t).
+// bott = bn1(conv1(x)):  w1t [C, R] (BN scale folded), b1 [R].  One thread per row (pixel, t), all R outputs in registers.
+// x is staged through shared memory in [128 rows x 64 channels] chunks with coalesced 16-byte loads (a thread reading its
+// own row straight from global touches 32 different rows per warp instruction); rows are padded by 16 B so that the
+// per-thread 16-byte reads are bank-conflict free.
+constexpr int kSqChunk = 64;
+template <typename T>
+constexpr int kSqRowBytes = kSqChunk * (int)sizeof(T) + 16;
+
 template <typename T, int R>
 __global__ void __launch_bounds__(kMseThreads) mse_squeeze_kernel(const T* __restrict__ x, const float* __restrict__ w1t,
                                                                   const float* __restrict__ b1, float* __restrict__ bott,
                                                                   size_t rows, int C) {
-    extern __shared__ __align__(16) float wsm[];  // [C][R]
+    extern __shared__ __align__(16) float wsm[];  // [C][R], then the x chunk
+    uint8_t* xs = reinterpret_cast<uint8_t*>(wsm + (size_t)C * R);
     for (int i = threadIdx.x; i < C * R / 4; i += kMseThreads)
         reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(w1t) + i);
-    __syncthreads();
-    const size_t row = (size_t)blockIdx.x * kMseThreads + threadIdx.x;
-    if (row >= rows) return;
+    const size_t row0 = (size_t)blockIdx.x * kMseThreads;
+    const size_t row = row0 + threadIdx.x;
     float acc[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) acc[j] = __ldg(b1 + j);
-    const T* xr = x + row * C;
-    for (int c8 = 0; c8 < C / 8; ++c8) {
-        float f[8];
-        load8(xr + c8 * 8, f);
+    constexpr int kVecPerRow = kSqChunk * (int)sizeof(T) / 16;   // 16-byte vectors per row of a chunk (8 bf16 / 16 fp32)
+    constexpr int kElemPerVec = 16 / (int)sizeof(T);
+    for (int c0 = 0; c0 < C; c0 += kSqChunk) {
+        __syncthreads();   // previous chunk consumed (and, first time, weights visible)
+        uint4 stage[kVecPerRow];   // all of this thread's loads are in flight before the first store
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4* wq = reinterpret_cast<const float4*>(wsm + (c8 * 8 + q) * R);
+        for (int i = 0; i < kVecPerRow; ++i) {
+            const int v = threadIdx.x + i * kMseThreads;
+            const int rr = v / kVecPerRow, cv = v % kVecPerRow;
+            const size_t gr = row0 + rr < rows ? row0 + rr : rows - 1;
+            stage[i] = *reinterpret_cast<const uint4*>(x + gr * C + c0 + cv * kElemPerVec);
+        }
 #pragma unroll
-            for (int j4 = 0; j4 < R / 4; ++j4) {
-                const float4 w = wq[j4];
-                acc[4 * j4 + 0] = fmaf(f[q], w.x, acc[4 * j4 + 0]);
-                acc[4 * j4 + 1] = fmaf(f[q], w.y, acc[4 * j4 + 1]);
-                acc[4 * j4 + 2] = fmaf(f[q], w.z, acc[4 * j4 + 2]);
-                acc[4 * j4 + 3] = fmaf(f[q], w.w, acc[4 * j4 + 3]);
+        for (int i = 0; i < kVecPerRow; ++i) {
+            const int v = threadIdx.x + i * kMseThreads;
+            *reinterpret_cast<uint4*>(xs + (v / kVecPerRow) * kSqRowBytes<T> + (v % kVecPerRow) * 16) = stage[i];
+        }
+        __syncthreads();
+        const T* xr = reinterpret_cast<const T*>(xs + threadIdx.x * kSqRowBytes<T>);
+#pragma unroll
+        for (int c8 = 0; c8 < kSqChunk / 8; ++c8) {
+            float f[8];
+            load8(xr + c8 * 8, f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4* wq = reinterpret_cast<const float4*>(wsm + (c0 + c8 * 8 + q) * R);
+#pragma unroll
+                for (int j4 = 0; j4 < R / 4; ++j4) {
+                    const float4 w = wq[j4];
+                    acc[4 * j4 + 0] = fmaf(f[q], w.x, acc[4 * j4 + 0]);
+                    acc[4 * j4 + 1] = fmaf(f[q], w.y, acc[4 * j4 + 1]);
+                    acc[4 * j4 + 2] = fmaf(f[q], w.z, acc[4 * j4 + 2]);
+                    acc[4 * j4 + 3] = fmaf(f[q], w.w, acc[4 * j4 + 3]);
+                }
             }
         }
     }
+    if (row >= rows) return;
     float4* o = reinterpret_cast<float4*>(bott + row * R);
 #pragma unroll
     for (int j4 = 0; j4 < R / 4; ++j4) o[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
@@ -180,21 +253,32 @@ __global__ void __launch_bounds__(kMseThreads) mse_diff_kernel(const float* __re
     float cb[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) cb[j] = 0.0f;
+#pragma unroll
     for (int dh = 0; dh < 3; ++dh) {
+        // the three taps of an image row are loaded unconditionally (coordinates clamped) and masked afterwards: a load
+        // inside a bounds-check branch is waited on in place, one L2 round trip per tap
         const int hh = h + dh - 1;
-        if ((unsigned)hh >= (unsigned)H) continue;
+        const int hc = min(max(hh, 0), H - 1);
+        float4 v[3][R / 4];
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+            const int wc = min(max(w + dw - 1, 0), W - 1);
+            const float4* src = reinterpret_cast<const float4*>(bott + ((((n * H + hc) * W + wc) * 8 + t) * (size_t)R));
+#pragma unroll
+            for (int j4 = 0; j4 < R / 4; ++j4) v[dw][j4] = src[j4];
+        }
+#pragma unroll
         for (int dw = 0; dw < 3; ++dw) {
             const int ww = w + dw - 1;
-            if ((unsigned)ww >= (unsigned)W) continue;
-            const float4* src = reinterpret_cast<const float4*>(bott + ((((n * H + hh) * W + ww) * 8 + t) * (size_t)R));
+            const float keep = ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) ? 1.0f : 0.0f;
             const float4* wk = reinterpret_cast<const float4*>(w2 + (dh * 3 + dw) * R);
 #pragma unroll
             for (int j4 = 0; j4 < R / 4; ++j4) {
-                const float4 v = src[j4], k = __ldg(wk + j4);
-                cb[4 * j4 + 0] = fmaf(v.x, k.x, cb[4 * j4 + 0]);
-                cb[4 * j4 + 1] = fmaf(v.y, k.y, cb[4 * j4 + 1]);
-                cb[4 * j4 + 2] = fmaf(v.z, k.z, cb[4 * j4 + 2]);
-                cb[4 * j4 + 3] = fmaf(v.w, k.w, cb[4 * j4 + 3]);
+                const float4 k = __ldg(wk + j4);
+                cb[4 * j4 + 0] = fmaf(v[dw][j4].x, k.x * keep, cb[4 * j4 + 0]);
+                cb[4 * j4 + 1] = fmaf(v[dw][j4].y, k.y * keep, cb[4 * j4 + 1]);
+                cb[4 * j4 + 2] = fmaf(v[dw][j4].z, k.z * keep, cb[4 * j4 + 2]);
+                cb[4 * j4 + 3] = fmaf(v[dw][j4].w, k.w * keep, cb[4 * j4 + 3]);
             }
         }
     }
@@ -262,23 +346,40 @@ __global__ void __launch_bounds__(kMseThreads) mse_small_kernel(const float* __r
     float acc[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) acc[j] = __ldg(bs + j);
+    constexpr int kI4 = R <= 16 ? R / 4 : 2;   // channel quads whose 4 x kI4 loads are in flight together
+#pragma unroll 1
     for (int dh = 0; dh < 3; ++dh) {
         const int hh = h2 + dh - 1;
-        if ((unsigned)hh >= (unsigned)H2) continue;
+        const int hc = min(max(hh, 0), H2 - 1);
+#pragma unroll 1
         for (int dw = 0; dw < 3; ++dw) {
             const int ww = w2 + dw - 1;
-            if ((unsigned)ww >= (unsigned)W2) continue;
-            const float4* s00 = reinterpret_cast<const float4*>(Dd + ((((n * H + 2 * hh) * W + 2 * ww) * 8 + t) * (size_t)R));
+            const int wc = min(max(ww, 0), W2 - 1);
+            const bool ok = (unsigned)hh < (unsigned)H2 && (unsigned)ww < (unsigned)W2;
+            const float4* s00 = reinterpret_cast<const float4*>(Dd + ((((n * H + 2 * hc) * W + 2 * wc) * 8 + t) * (size_t)R));
             const float4* s01 = s00 + 8 * R / 4;
             const float4* s10 = s00 + (size_t)W * 8 * R / 4;
             const float4* s11 = s10 + 8 * R / 4;
             const float* wt = wsm + (dh * 3 + dw) * R * R;
 #pragma unroll
-            for (int i4 = 0; i4 < R / 4; ++i4) {
-                const float4 a = s00[i4], b = s01[i4], c = s10[i4], d = s11[i4];
-                const float4 pooled = make_float4(((a.x + b.x) + (c.x + d.x)) * 0.25f, ((a.y + b.y) + (c.y + d.y)) * 0.25f,
-                                                  ((a.z + b.z) + (c.z + d.z)) * 0.25f, ((a.w + b.w) + (c.w + d.w)) * 0.25f);
-                fma_rows4<R>(acc, pooled, wt + i4 * 4 * R);
+            for (int i0 = 0; i0 < R / 4; i0 += kI4) {
+                float4 a[kI4], b[kI4], c[kI4], d[kI4];
+#pragma unroll
+                for (int i = 0; i < kI4; ++i) {   // unconditional (clamped) loads, masked use
+                    a[i] = s00[i0 + i];
+                    b[i] = s01[i0 + i];
+                    c[i] = s10[i0 + i];
+                    d[i] = s11[i0 + i];
+                }
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < kI4; ++i) {
+                        const float4 pooled =
+                            make_float4(((a[i].x + b[i].x) + (c[i].x + d[i].x)) * 0.25f, ((a[i].y + b[i].y) + (c[i].y + d[i].y)) * 0.25f,
+                                        ((a[i].z + b[i].z) + (c[i].z + d[i].z)) * 0.25f, ((a[i].w + b[i].w) + (c[i].w + d[i].w)) * 0.25f);
+                        fma_rows4<R>(acc, pooled, wt + (i0 + i) * 4 * R);
+                    }
+                }
             }
         }
     }
@@ -358,30 +459,42 @@ __global__ void __launch_bounds__(kMseThreads) mse_gate_shift_kernel(const T* __
         }
     }
     __syncthreads();
-    // phase 2: thread = channel pair (x2 loads / stores); when C/2 < 128 the block's pixels are split between thread groups
-    const int CP = C / 2;
-    const int groups = CP < kMseThreads ? kMseThreads / CP : 1;
+    // phase 2: thread = NCH adjacent channels (one vector load / store per row); when there are fewer channel groups than
+    // threads the block's pixels are split between thread groups
+    constexpr int NCH = R <= 8 ? 4 : 2;   // wider only where the conv3 weights of 4 channels fit in registers at full occupancy
+    const int CG = C / NCH;
+    const int groups = CG < kMseThreads ? kMseThreads / CG : 1;
     const int per_group = kGatePixels / groups;
-    const int pg = CP < kMseThreads ? threadIdx.x / CP : 0;
-    for (int cp = CP < kMseThreads ? threadIdx.x % CP : threadIdx.x; cp < CP; cp += kMseThreads) {
-        const int c = 2 * cp;
-        float w3a[R], w3b[R];
+    const int pg = CG < kMseThreads ? threadIdx.x / CG : 0;
+    for (int cg = CG < kMseThreads ? threadIdx.x % CG : threadIdx.x; cg < CG; cg += kMseThreads) {
+        const int c = NCH * cg;
+        float w3[NCH][R], b3[NCH], k0[NCH], k1[NCH], k2[NCH];
 #pragma unroll
         for (int ji = 0; ji < R; ++ji) {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(a.w3t + (size_t)ji * C + c));
-            w3a[ji] = w.x;
-            w3b[ji] = w.y;
+            float w[NCH];
+            loadN<NCH>(a.w3t + (size_t)ji * C + c, w);
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) w3[q][ji] = w[q];
         }
-        const float b3a = __ldg(a.b3 + c), b3b = __ldg(a.b3 + c + 1);
-        const float ka0 = __ldg(a.wsh + c * 3), ka1 = __ldg(a.wsh + c * 3 + 1), ka2 = __ldg(a.wsh + c * 3 + 2);
-        const float kb0 = __ldg(a.wsh + c * 3 + 3), kb1 = __ldg(a.wsh + c * 3 + 4), kb2 = __ldg(a.wsh + c * 3 + 5);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            b3[q] = __ldg(a.b3 + c + q);
+            k0[q] = __ldg(a.wsh + (c + q) * 3);
+            k1[q] = __ldg(a.wsh + (c + q) * 3 + 1);
+            k2[q] = __ldg(a.wsh + (c + q) * 3 + 2);
+        }
         for (int pl = pg * per_group; pl < (pg + 1) * per_group; ++pl) {
             const size_t p = p0 + pl;
             if (p >= P) break;
-            float oa[8], ob[8];
+            float xs[8][NCH];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) loadN<NCH>(x + (p * 8 + t) * (size_t)C + c, xs[t]);   // eight loads in flight
+            float o[8][NCH];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                float yfa = b3a, yba = b3a, yfb = b3b, ybb = b3b;
+                float yf[NCH], yb[NCH];
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) yf[q] = yb[q] = b3[q];
                 const float4* mf = reinterpret_cast<const float4*>(ms + ((pl * 2 + 0) * 8 + t) * R);
                 const float4* mb = reinterpret_cast<const float4*>(ms + ((pl * 2 + 1) * 8 + t) * R);
 #pragma unroll
@@ -389,33 +502,34 @@ __global__ void __launch_bounds__(kMseThreads) mse_gate_shift_kernel(const T* __
                     const float4 f = mf[j4], b = mb[j4];
                     const float fv[4] = {f.x, f.y, f.z, f.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        yfa = fmaf(w3a[4 * j4 + q], fv[q], yfa);
-                        yba = fmaf(w3a[4 * j4 + q], bv[q], yba);
-                        yfb = fmaf(w3b[4 * j4 + q], fv[q], yfb);
-                        ybb = fmaf(w3b[4 * j4 + q], bv[q], ybb);
-                    }
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int q = 0; q < NCH; ++q) {
+                            yf[q] = fmaf(w3[q][4 * j4 + u], fv[u], yf[q]);
+                            yb[q] = fmaf(w3[q][4 * j4 + u], bv[u], yb[q]);
+                        }
                 }
-                // y = 0.5 (sigmoid(yf) - 0.5) + 0.5 (sigmoid(yb) - 0.5)
-                const float ga = 0.5f * (__fdividef(1.0f, 1.0f + __expf(-yfa)) + __fdividef(1.0f, 1.0f + __expf(-yba))) - 0.5f;
-                const float gb = 0.5f * (__fdividef(1.0f, 1.0f + __expf(-yfb)) + __fdividef(1.0f, 1.0f + __expf(-ybb))) - 0.5f;
-                float xa, xb;
-                load2(x + (p * 8 + t) * (size_t)C + c, xa, xb);
-                oa[t] = xa + xa * ga;
-                ob[t] = xb + xb * gb;
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    // y = 0.5 (sigmoid(yf) - 0.5) + 0.5 (sigmoid(yb) - 0.5); sigmoid(v) - 0.5 = 0.5 tanh(v / 2)
+                    float g;
+                    if (sizeof(T) == 2)   // bf16 path: MUFU.TANH (abs err ~5e-4 on the gate, far below one bf16 ulp of x)
+                        g = 0.25f * (tanh_approx(0.5f * yf[q]) + tanh_approx(0.5f * yb[q]));
+                    else
+                        g = 0.5f * (__fdividef(1.0f, 1.0f + __expf(-yf[q])) + __fdividef(1.0f, 1.0f + __expf(-yb[q]))) - 0.5f;
+                    o[t][q] = xs[t][q] + xs[t][q] * g;
+                }
             }
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                float va = ka1 * oa[t], vb = kb1 * ob[t];
-                if (t > 0) {
-                    va = fmaf(ka0, oa[t - 1], va);
-                    vb = fmaf(kb0, ob[t - 1], vb);
+                float v[NCH];
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    v[q] = k1[q] * o[t][q];
+                    if (t > 0) v[q] = fmaf(k0[q], o[t - 1][q], v[q]);
+                    if (t < 7) v[q] = fmaf(k2[q], o[t + 1][q], v[q]);
                 }
-                if (t < 7) {
-                    va = fmaf(ka2, oa[t + 1], va);
-                    vb = fmaf(kb2, ob[t + 1], vb);
-                }
-                store2(out + (p * 8 + t) * (size_t)C + c, va, vb);
+                storeN<NCH>(out + (p * 8 + t) * (size_t)C + c, v);
             }
         }
     }
