@@ -22,6 +22,7 @@
 #include "wd_conv_2cta.cuh"
 #include "wd_stem_pool.cuh"
 #include "wd_tdn_kernels.cuh"
+#include "wd_conv_fuse2.cuh"
 
 namespace {
 
@@ -119,6 +120,7 @@ struct ConvLayer {
     int fuse_stride = 1;    // stride of the folded downsample (2: the second A source is sampled at every other pixel)
     int fuse_ds = -1;       // conv3 of a block 0: index of the downsample conv folded into its K dimension
     bool fused_away = false; // downsample conv that runs inside the block's conv3 (kept for its weights)
+    bool fused_next = false; // conv1 that runs inside the previous block's conv3 kernel (kept for its weights / maps)
     int kb_split = 0;       // fused conv3: k-blocks [0, kb_split) come from the block's conv2 output, the rest from the
                             // block input (second A map)
     // device data
@@ -151,6 +153,8 @@ struct Op {
     int out_buf = -1;
     int res_buf = -1;        // residual buffer or -1
     int in2_buf = -1;        // fused downsample: the block input (second A source)
+    int conv2 = -1;          // layer 1: conv1 of the NEXT block, computed by the same kernel (wd_conv_fuse2.cuh)
+    int out2_buf = -1;       // ... and the buffer its output goes to
     std::string name;
     int C = 0, H = 0, W = 0;  // output dims per frame
     int Hy = 0;               // OP_BLEND: resolution of the up-sampled operand
@@ -168,6 +172,8 @@ struct wd_engine {
     int use_strip = 1;
     int fuse_ds = 2;
     int fuse_ds_requested = 2;  // WD_FUSE_DS at create time
+    int fuse2 = 1;              // layer-1 conv3 + next conv1 in one kernel (needs fuse_ds >= 1 and 256-wide tiles)
+    int fuse2_requested = 1;    // WD_FUSE2 at create time
     int stem_seg_rows = 28;  // pooled rows per work unit of the fused stem + max-pool kernel
     int sm_count = 148;
     std::vector<ConvLayer> convs;
@@ -273,6 +279,7 @@ int build_plan(wd_engine* e) {
     int cur = 1;
     int H = e->convs[ci].Hout / 2;
     int inplanes = 64;
+    int pre_c1 = -1, pre_buf = -1;  // conv1 of the coming block already scheduled inside the previous conv3 kernel
     for (int L = 0; L < 4; ++L) {
         for (int b = 0; b < blocks[L]; ++b) {
             const int stride = (L > 0 && b == 0) ? 2 : 1;
@@ -280,16 +287,37 @@ int build_plan(wd_engine* e) {
             const int outp = width * 4;
             const std::string pre = "base_model.layer" + std::to_string(L + 1) + "." + std::to_string(b);
             const std::string nm = "layer" + std::to_string(L + 1) + "." + std::to_string(b);
-            int fr[3], nf = 0;
-            for (int i = 0; i < 4; ++i)
-                if (i != cur) fr[nf++] = i;
+            // buffers: b1 = conv1 output (and, once conv2 has consumed it, conv3 output), o0 = conv2 output, o1 = spare
+            // (un-fused downsample, or the NEXT block's conv1 output when that conv runs inside this block's conv3 kernel)
+            int b1, o0, o1;
+            if (pre_buf >= 0) {
+                b1 = pre_buf;
+                int rest[2], nr = 0;
+                for (int i = 0; i < 4; ++i)
+                    if (i != cur && i != b1) rest[nr++] = i;
+                o0 = rest[0];
+                o1 = rest[1];
+            } else {
+                int fr[3], nf = 0;
+                for (int i = 0; i < 4; ++i)
+                    if (i != cur) fr[nf++] = i;
+                b1 = fr[0];
+                o0 = fr[1];
+                o1 = fr[2];
+            }
             const int fold = e->desc.is_shift ? inplanes / e->desc.shift_div : 0;
-            const int c1 = add_conv(nm + ".conv1", pre + ".conv1.net.weight", pre + ".conv1.weight", pre + ".bn1",
-                                    inplanes, width, 1, 1, H, fold, 1);
-            add_conv_op(c1, cur, fr[0], -1);
+            int c1;
+            if (pre_c1 >= 0) {
+                c1 = pre_c1;   // created (and scheduled) with the previous block's conv3
+            } else {
+                c1 = add_conv(nm + ".conv1", pre + ".conv1.net.weight", pre + ".conv1.weight", pre + ".bn1", inplanes,
+                              width, 1, 1, H, fold, 1);
+                add_conv_op(c1, cur, b1, -1);
+            }
+            pre_c1 = pre_buf = -1;
             const int c2 = add_conv(nm + ".conv2", pre + ".conv2.weight", "", pre + ".bn2", width, width, 3, stride,
                                     H, 0, 1);
-            add_conv_op(c2, fr[0], fr[1], -1);
+            add_conv_op(c2, b1, o0, -1);
             const int Ho = e->convs[c2].Hout;
             int idbuf = cur;
             // Block 0 of layer 1 (stride 1): out = relu(W3*y2 + b3 + Wd*x + bd) is ONE GEMM over the concatenated
@@ -303,8 +331,8 @@ int build_plan(wd_engine* e) {
                 if (fuse) {
                     e->convs[cd].fused_away = true;
                 } else {
-                    add_conv_op(cd, cur, fr[2], -1);
-                    idbuf = fr[2];
+                    add_conv_op(cd, cur, o1, -1);
+                    idbuf = o1;
                 }
             }
             const int c3 =
@@ -312,13 +340,29 @@ int build_plan(wd_engine* e) {
             if (fuse) {
                 e->convs[c3].fuse_ds = cd;
                 e->convs[c3].fuse_stride = stride;
-                add_conv_op(c3, fr[1], fr[0], -1);
+                add_conv_op(c3, o0, b1, -1);
                 e->ops.back().in2_buf = cur;
                 e->ops.back().macs_per_clip += 8.0 * Ho * Ho * (double)outp * inplanes;
             } else {
-                add_conv_op(c3, fr[1], fr[0], idbuf);  // conv1's buffer is free again
+                add_conv_op(c3, o0, b1, idbuf);  // conv1's buffer is free again
             }
-            cur = fr[0];
+            // Layer 1: conv1 of the next block (256 -> 64, HBM-bound on re-reading this block's output) runs inside this
+            // block's conv3 kernel, from the bf16 tile in tensor memory (wd_conv_fuse2.cuh).
+            if (e->fuse2 && L == 0 && e->desc.mode == WD_MODE_BF16 && e->fuse_ds >= 1 && e->desc.is_shift && outp == 256 &&
+                outp / e->desc.shift_div == 32 && (b > 0 || fuse) && (b + 1 < blocks[L] || e->fuse2 >= 2)) {
+                const bool last = b + 1 == blocks[L];   // the next conv1 is layer2.0.conv1 (256 -> 128, still 56 x 56)
+                const std::string nb = last ? "layer2.0" : "layer1." + std::to_string(b + 1);
+                pre_c1 = add_conv(nb + ".conv1", "base_model." + nb + ".conv1.net.weight", "base_model." + nb + ".conv1.weight",
+                                  "base_model." + nb + ".bn1", outp, last ? planes[1] : width, 1, 1, Ho,
+                                  outp / e->desc.shift_div, 1);
+                e->convs[pre_c1].fused_next = true;
+                pre_buf = o1;
+                Op& o3 = e->ops.back();
+                o3.conv2 = pre_c1;
+                o3.out2_buf = o1;
+                o3.macs_per_clip += 8.0 * Ho * Ho * (double)e->convs[pre_c1].Cout * outp;
+            }
+            cur = b1;
             H = Ho;
             inplanes = outp;
         }
@@ -1147,6 +1191,53 @@ int launch_stem_pool(wd_engine* e, const ConvLayer& c, const void* frames, void*
 }
 
 
+// Layer 1: conv3 of a block + conv1 of the next block in one kernel (wd_conv_fuse2.cuh).  c3's maps (W, A, second A
+// source, output, residual) are the ones load_weights built for the plain kernel; c1n contributes W, bias and the z map.
+template <bool RES, int N2>
+int launch_fuse2_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int n_clips, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_fuse2_kernel<RES, N2>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Fuse2Args p{};
+    p.bias1 = c3.bias;
+    p.bias2 = c1n.bias;
+    p.M = n_clips * c3.Hout * c3.Wout * 8;
+    p.num_tiles = (p.M + wd::kTileM - 1) / wd::kTileM;
+    p.kblocks = c3.kblocks;
+    p.kb_split = c3.kb_split;
+    // shared memory: A ring | W3 (resident) | W1' (resident) | 8 output slabs | residual ring | barriers + biases
+    const int fixed = p.kblocks * 256 * 128 + N2 * 256 * 2 + 8 * wd::kEpiSlab + 2048 + 1024;
+    p.res_depth = RES ? wd::kF2ResDepth : 0;
+    p.a_stages = 4;
+    while (p.a_stages > 2 && fixed + p.a_stages * wd::kATileBytes + 4 * p.res_depth * wd::kEpiSlab > 232448) --p.a_stages;
+    if (RES && fixed + p.a_stages * wd::kATileBytes + 4 * p.res_depth * wd::kEpiSlab > 232448) p.res_depth = 2;
+    p.off_w1 = p.a_stages * wd::kATileBytes;
+    p.off_w2 = p.off_w1 + p.kblocks * 256 * 128;
+    p.off_out = p.off_w2 + N2 * 256 * 2;
+    p.off_res = p.off_out + 8 * wd::kEpiSlab;
+    p.off_bar = p.off_res + 4 * p.res_depth * wd::kEpiSlab;
+    const size_t smem = (size_t)p.off_bar + 2048 + 1024;
+    if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1: %zu bytes of shared memory", smem);
+    const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
+    WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kF2Threads, smem, st, c3.wmap, c1n.wmap, c3.amap, c3.amap32, c3.omap,
+                       RES ? c3.rmap : c3.omap, c1n.omap, p));
+    return WD_OK;
+}
+
+// Layer 1: conv3 of a block + conv1 of the next block in one kernel (wd_conv_fuse2.cuh).  c3's maps (W, A, second A
+// source, output, residual) are the ones load_weights built for the plain kernel; c1n contributes W, bias and the z map.
+int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool has_res, int n_clips, cudaStream_t st) {
+    if (c3.tile_n != 256 || c3.Cout != 256 || (c1n.Cout != 64 && c1n.Cout != 128) || c1n.tile_n != c1n.Cout ||
+        c1n.Cin != 256 || c1n.fold != 32 || c3.a_mode != wd::A_TMA || c3.kblocks < 1 || c3.kblocks > 2)
+        return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused conv3 + conv1 kernel", c3.name.c_str(), c1n.name.c_str());
+    if (c1n.Cout == 64)
+        return has_res ? launch_fuse2_t<true, 64>(e, c3, c1n, n_clips, st) : launch_fuse2_t<false, 64>(e, c3, c1n, n_clips, st);
+    return has_res ? launch_fuse2_t<true, 128>(e, c3, c1n, n_clips, st) : launch_fuse2_t<false, 128>(e, c3, c1n, n_clips, st);
+}
+
 // Motion excitation + temporal Conv1d of one BottleneckShift: four launches (wd_tdn_kernels.cuh).
 template <typename T, int R>
 int launch_mse(const MseLayer& ml, const void* in, void* out, float* scratch, int n_clips, cudaStream_t st) {
@@ -1225,6 +1316,8 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 dim3 grid((a.M + 3) / 4, (c.Cout + 63) / 64);
                 wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
                 WD_CUDA(cudaGetLastError());
+            } else if (o.conv2 >= 0) {
+                WD_TRY(launch_fuse2(e, c, e->convs[o.conv2], res != nullptr, n_clips, st));
             } else if (o.in_buf == kInDiff && c.a_mode == wd::A_TAP) {
                 ConvLayer cc = c;  // tap boxes over the caller's difference tensor: its address is known only now
                 WD_TRY(make_amap_tap(&cc.amap, in, c.Cin, c.Win, c.Hin, (size_t)n_clips, 1, wd::kStripPixels));
@@ -1412,6 +1505,8 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
     e->fuse_ds_requested = getenv("WD_FUSE_DS") ? atoi(getenv("WD_FUSE_DS")) : 2;  // 0 off, 1 layer1.0, 2 + the stride-2 blocks
     e->fuse_ds = e->fuse_ds_requested;
+    e->fuse2_requested = getenv("WD_FUSE2") ? atoi(getenv("WD_FUSE2")) : 2;  // 1: inside layer 1, 2: + layer2.0.conv1
+    e->fuse2 = e->fuse2_requested;
     int r = d->arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e);
     if (r != WD_OK) {
         delete e;
@@ -1506,7 +1601,8 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     // downsample into conv3 needs the v4 kernel and the TMA A path.  Rebuild the plan when they disagree.
     {
         const int want_fuse = (e->use_tma_a && e->persistent >= 3) ? e->fuse_ds_requested : 0;
-        if (want_fuse != e->fuse_ds) {
+        const int want_f2 = (want_fuse >= 1 && e->tile_n_max == 256) ? e->fuse2_requested : 0;
+        if (want_fuse != e->fuse_ds || want_f2 != e->fuse2) {
             for (auto& c : e->convs) {
                 if (c.w_packed) cudaFree(c.w_packed);
                 if (c.bias) cudaFree(c.bias);
@@ -1518,6 +1614,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                     if (q) cudaFree(q);
             e->mses.clear();
             e->fuse_ds = want_fuse;
+            e->fuse2 = want_f2;
             e->tap_idx = -1;
             WD_TRY(e->desc.arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e));
         }
@@ -1603,6 +1700,8 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             const size_t rows = (size_t)e->desc.max_clips * c.Hout * c.Wout * 8;
             WD_TRY(make_omap(&c.omap, e->buf[o.out_buf], c.Cout, rows));
             if (o.res_buf >= 0) WD_TRY(make_omap(&c.rmap, e->buf[o.res_buf], c.Cout, rows));
+            if (o.conv2 >= 0)   // the next block's conv1 output, written by the same kernel
+                WD_TRY(make_omap(&e->convs[o.conv2].omap, e->buf[o.out2_buf], e->convs[o.conv2].Cout, rows));
             if (c.a_mode == wd::A_STRIP) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
                 WD_TRY(make_amap5(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
