@@ -257,12 +257,13 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_step")
-    # "launch" here = the tcgen05 launches of one step taken together (48 convolutions, the four block-0 downsamples
-    # folded into their conv3's K dimension, + stem_pool_kernel = 49):
+    # "launch" here = the tcgen05 launches of one step taken together (45 convolution kernels: the four block-0
+    # downsamples are folded into their conv3's K dimension, three conv1s run inside the preceding conv3 kernel;
+    # + stem_pool_kernel = 46):
     # achieved = their algorithmic FLOPs / the sum of their CUDA-event durations; traffic = their summed DRAM bytes.
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["sustained"], traffic=traffic,
-                    kernel=f"the {n_tc} tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), stem_pool_kernel",
+                    kernel=f"the {n_tc} tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), conv_fuse2_kernel (layer 1: conv3 + next conv1), stem_pool_kernel",
                     frac_of_burst=achieved / peaks["burst"], peak_source=peaks["source"],
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / max(sum(op_ms), 1e-9),
                     dram_gbs=(traffic / (conv_ms * 1e-3) / 1e9) if traffic else None,

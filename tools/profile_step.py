@@ -1,5 +1,5 @@
-"""Minimal program for ncu: one warm-up and one measured forward of the hot path at batch 64 (56 launches each:
-preprocess, stem+max-pool, 48 convs, head = 51 launches). Usage under ncu: see profiles/README.md."""
+"""Minimal program for ncu: one warm-up and one measured forward of the hot path at batch 64 (48 launches each:
+preprocess, stem+max-pool, 45 conv kernels, head). Usage under ncu: see profiles/README.md."""
 import os
 import sys
 
