@@ -697,3 +697,25 @@ def test_engine_session_ort_surface(weights, tsm_gold):
         want = torch.softmax(O.tsm_forward(sd11, x), 1).numpy()
     assert p11.shape == (2, 11) and abs(float(p11.sum()) - 2.0) < 1e-4
     assert float(np.abs(p11 - want).max()) < TOL_BF16
+
+
+def test_fused_conv3_conv1_equals_unfused(weights):
+    """conv_fuse2_kernel (layer-1 conv3 + the next block's conv1, A operand of the second MMA in tensor memory,
+    TemporalShift as a warp shuffle) against the same network with the two convolutions as separate kernels
+    (WD_FUSE2=0): same bf16 products, same fp32 accumulation order -> bit-identical logits."""
+    from workoutdetector_b200.engine import Engine
+    x = torch.randn(5 * 8, 3, 224, 224, generator=torch.Generator().manual_seed(21)).cuda()
+    out = {}
+    for flag in ("2", "1", "0"):
+        os.environ["WD_FUSE2"] = flag
+        try:
+            e = Engine(12, max_clips=5)
+        finally:
+            del os.environ["WD_FUSE2"]
+        e.load_state_dict(weights["rand"])
+        names = [o["name"] for o in e.ops()]
+        assert ("layer1.1.conv1" in names) == (flag == "0") and ("layer2.0.conv1" in names) == (flag != "2")
+        assert len(names) == {"2": 47, "1": 48, "0": 50}[flag]
+        out[flag] = e.forward(e.pack_nchw(x))[0].clone()
+        e.close()
+    assert torch.equal(out["2"], out["0"]) and torch.equal(out["1"], out["0"])

@@ -67,6 +67,7 @@ struct Fuse2Args {
     int kb_split;         // k-blocks >= kb_split come from the second A map (0 = none)
     int a_stages;
     int res_depth;        // residual slabs in flight per epilogue warp (2 or 3)
+    int shift;            // 1: the second convolution sees TemporalShift(y) with fold 32 (TSM); 0: y itself (TDN layer 1)
     int off_w1, off_w2, off_out, off_res, off_bar;   // byte offsets; the A ring starts at 0
 };
 
@@ -232,7 +233,7 @@ conv_fuse2_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], box
                     tma_store_commit();
                 }
                 __syncwarp();
-                if (c == 0) {
+                if (c == 0 && a.shift) {
                     // TemporalShift of the next conv1 (fold 32 of 256 channels): channels 0..31 come from segment t+1,
                     // 32..63 from t-1, zeros at the ends; the 8 segments of a pixel are 8 adjacent lanes
 #pragma unroll

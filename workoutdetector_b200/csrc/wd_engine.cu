@@ -440,16 +440,29 @@ int build_plan_tdn(wd_engine* e) {
         o.Hy = Hy;
         e->ops.push_back(o);
     };
-    // one bottleneck; returns the buffer holding its output
+    // one bottleneck; returns the buffer holding its output.  next_pre / next_nm (layer 1 only): the following block of
+    // the same layer, whose conv1 then runs inside this block's conv3 kernel (wd_conv_fuse2.cuh) and is skipped there.
+    int pre_c1 = -1, pre_buf = -1;
     auto bottleneck = [&](const std::string& pre, const std::string& nm, int inplanes, int width, int stride, int H,
-                          bool mse, bool has_ds, int cur, int held) -> int {
+                          bool mse, bool has_ds, int cur, int held, const std::string& next_pre,
+                          const std::string& next_nm) -> int {
         int fr[3], nf = 0;
         for (int i = 0; i < kScratch && nf < 3; ++i)
-            if (i != cur && i != held) fr[nf++] = i;
+            if (i != cur && i != held && i != pre_buf) fr[nf++] = i;
         const int outp = width * 4;
-        const int c1 = add_conv(nm + ".conv1", pre + ".conv1", pre + ".bn1", inplanes, width, 1, 1, H, 1, true);
-        add_conv_op(c1, cur, fr[0], -1);
-        int y = fr[0], other = fr[1];
+        int y, other, spare;
+        if (pre_c1 >= 0) {   // conv1 already scheduled with the previous block's conv3
+            y = pre_buf;
+            other = fr[0];
+            spare = fr[1];
+        } else {
+            y = fr[0];
+            other = fr[1];
+            spare = fr[2];
+            const int c1 = add_conv(nm + ".conv1", pre + ".conv1", pre + ".bn1", inplanes, width, 1, 1, H, 1, true);
+            add_conv_op(c1, cur, y, -1);
+        }
+        pre_c1 = pre_buf = -1;
         if (mse) {
             MseLayer m;
             m.prefix = pre;
@@ -483,8 +496,8 @@ int build_plan_tdn(wd_engine* e) {
             if (fuse) {
                 e->convs[cd].fused_away = true;
             } else {
-                add_conv_op(cd, cur, fr[2], -1);
-                idbuf = fr[2];
+                add_conv_op(cd, cur, spare, -1);
+                idbuf = spare;
             }
         }
         const int c3 = add_conv(nm + ".conv3", pre + ".conv3", pre + ".bn3", width, outp, 1, 1, Ho, 1, true);
@@ -497,6 +510,15 @@ int build_plan_tdn(wd_engine* e) {
         } else {
             add_conv_op(c3, y, other, idbuf);
         }
+        if (e->fuse2 && bf && e->fuse_ds >= 1 && !next_pre.empty() && !mse && outp == 256 && width == 64 && (!has_ds || fuse)) {
+            pre_c1 = add_conv(next_nm + ".conv1", next_pre + ".conv1", next_pre + ".bn1", outp, width, 1, 1, Ho, 1, true);
+            e->convs[pre_c1].fused_next = true;
+            pre_buf = spare;
+            Op& o3 = e->ops.back();
+            o3.conv2 = pre_c1;
+            o3.out2_buf = spare;
+            o3.macs_per_clip += 8.0 * Ho * Ho * (double)width * outp;
+        }
         return other;
     };
     auto layer = [&](const std::string& prefix, const std::string& name, int L, int H, bool mse, int cur, int held,
@@ -504,8 +526,11 @@ int build_plan_tdn(wd_engine* e) {
         int inplanes = L == 0 ? 64 : planes[L - 1] * 4;
         for (int b = 0; b < blocks[L]; ++b) {
             const int stride = (L > 0 && b == 0) ? 2 : 1;
+            const bool nxt = L == 0 && b + 1 < blocks[L];
             cur = bottleneck("base_model." + prefix + "." + std::to_string(b), name + "." + std::to_string(b), inplanes,
-                             planes[L], stride, H, mse, b == 0, cur, held);
+                             planes[L], stride, H, mse, b == 0, cur, held,
+                             nxt ? "base_model." + prefix + "." + std::to_string(b + 1) : std::string(),
+                             nxt ? name + "." + std::to_string(b + 1) : std::string());
             if (stride == 2) H /= 2;
             inplanes = planes[L] * 4;
         }
@@ -1208,6 +1233,7 @@ int launch_fuse2_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
     p.num_tiles = (p.M + wd::kTileM - 1) / wd::kTileM;
     p.kblocks = c3.kblocks;
     p.kb_split = c3.kb_split;
+    p.shift = c1n.fold == 32 ? 1 : 0;
     // shared memory: A ring | W3 (resident) | W1' (resident) | 8 output slabs | residual ring | barriers + biases
     const int fixed = p.kblocks * 256 * 128 + N2 * 256 * 2 + 8 * wd::kEpiSlab + 2048 + 1024;
     p.res_depth = RES ? wd::kF2ResDepth : 0;
@@ -1231,7 +1257,7 @@ int launch_fuse2_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
 // source, output, residual) are the ones load_weights built for the plain kernel; c1n contributes W, bias and the z map.
 int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool has_res, int n_clips, cudaStream_t st) {
     if (c3.tile_n != 256 || c3.Cout != 256 || (c1n.Cout != 64 && c1n.Cout != 128) || c1n.tile_n != c1n.Cout ||
-        c1n.Cin != 256 || c1n.fold != 32 || c3.a_mode != wd::A_TMA || c3.kblocks < 1 || c3.kblocks > 2)
+        c1n.Cin != 256 || (c1n.fold != 32 && c1n.fold != 0) || c3.a_mode != wd::A_TMA || c3.kblocks < 1 || c3.kblocks > 2)
         return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused conv3 + conv1 kernel", c3.name.c_str(), c1n.name.c_str());
     if (c1n.Cout == 64)
         return has_res ? launch_fuse2_t<true, 64>(e, c3, c1n, n_clips, st) : launch_fuse2_t<false, 64>(e, c3, c1n, n_clips, st);
