@@ -2000,14 +2000,16 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
         if (e->h_idx >= 2) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
         WD_CUDA(cudaMemcpyAsync(e->h_u8[slot], host + (size_t)done * clip_bytes, (size_t)nc * clip_bytes,
                                 cudaMemcpyHostToDevice, cp));
+        // resize / normalise on the copy stream as well: it overlaps the previous chunk's convolutions (its CTAs fit
+        // beside the persistent one-per-SM convolution CTAs) instead of extending the compute stream's critical path
+        WD_TRY(preprocess_impl(e->desc.mode, e->h_u8[slot], nc * 8, H, W, nullptr, nc * 8, in_scale,
+                               e->h_frames[slot], cp));
+        ++e->launches;
         cudaEvent_t copied;
         WD_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
         WD_CUDA(cudaEventRecord(copied, cp));
         WD_CUDA(cudaStreamWaitEvent(cs, copied, 0));
         WD_CUDA(cudaEventDestroy(copied));
-        WD_TRY(preprocess_impl(e->desc.mode, e->h_u8[slot], nc * 8, H, W, nullptr, nc * 8, in_scale,
-                               e->h_frames[slot], cs));
-        ++e->launches;
         WD_TRY(run_forward(e, e->h_frames[slot], nc, e->h_logits + (size_t)done * C, e->h_probs + (size_t)done * C,
                            e->h_state + done, threshold, apply_softmax, cs, nullptr));
         WD_CUDA(cudaEventRecord(e->hevent[slot], cs));
