@@ -54,3 +54,21 @@ out = os.environ.get("WD_OUT")
 if out:
     with open(out, "w") as f:
         json.dump(dict(batch=B, ms=tot, ops=rows), f, indent=1)
+# whole-forward loops (no per-op events): forward alone, preprocess + forward
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def loop(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(n):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / n
+
+
+print(f"forward alone          {loop(lambda: eng.forward(frames)):.3f} ms")
+print(f"preprocess + forward   {loop(lambda: eng.forward(eng.preprocess_u8(u8))):.3f} ms")
