@@ -168,8 +168,13 @@ int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int
 int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems);
 /* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (conv kernel generation: 0 one tile per CTA, 1 v2,
  * 2 v3, 3 v4 = default), "use_strip" (0/1: row-strip A operand for 3x3 stride-1 convolutions, v3/v4),
- * "stem_seg_rows" (pooled rows per work unit of the fused stem, divides 56).  Takes effect at the next
- * wd_engine_load_weights. */
+ * "stem_seg_rows" (pooled rows per work unit of the fused stem, divides 56), "use_2cta" (CTA-pair kernels: 0 off,
+ * 1 1x1 conv1, 2 + 3x3 strips, 3 + tap boxes, 4 + residual conv3 = default, 5 + narrow N = 64 strips (slower, kept for
+ * measurements)), "pdl" (0/1 programmatic dependent launch), "prefetch_kblocks" (-1 = per-layer rule).  Takes effect
+ * at the next wd_engine_load_weights.
+ * Environment switches read at wd_engine_create (A/B measurements and differential tests): WD_FUSE_DS (0 / 1 / 2: fold
+ * the block-0 downsample into conv3: off / layer 1 / all layers, default 2), WD_FUSE2 (0 / 1 / 2: layer-1 conv3 + the next
+ * conv1 in one kernel: off / inside layer 1 / + layer2.0.conv1, default 2), WD_HEAD_SPLIT (0 / 1), WD_HOST_CHUNK. */
 int wd_engine_set_option(wd_engine* e, const char* key, int value);
 /* Number of kernels the engine launched since creation (all are this library's own kernels). */
 int64_t wd_engine_launch_count(const wd_engine* e);
