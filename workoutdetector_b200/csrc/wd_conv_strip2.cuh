@@ -1,0 +1,228 @@
+// wd_conv_strip2.cuh — 3x3 stride-1 convolution with 64 input and 64 output channels (conv2 of the layer-1 bottlenecks),
+// TWO output rows per tile (sm_100a).
+//
+// Why: a 128 x N x 16 tcgen05.mma costs max(76, N/2) cycles (tools/microbench/mma_issue.cu): with Cout = 64 every MMA of
+// the one-row strip kernel (conv_v4_kernel<64, A_STRIP>) runs at 42 % of the tensor rate, 36 MMAs per 14-pixel strip.
+// An input row feeds up to three output rows; computing output rows h and h+1 together, the two middle input rows
+// (h, h+1) update BOTH accumulators with one N = 128 instruction — which costs the same 76 cycles — and only the outer
+// rows (h-1, h+2) need N = 64 ones: 48 MMAs per two strips instead of 72, and four input-row loads per two strips
+// instead of six.
+//
+//   D[h]   = sum_s  A[h-1,s] W[0,s] + A[h,s] W[1,s] + A[h+1,s] W[2,s]
+//   D[h+1] = sum_s                    A[h,s] W[0,s] + A[h+1,s] W[1,s] + A[h+2,s] W[2,s]
+//
+// Weights sit in shared memory as [s][W2 | W1 | W0] (8 KiB each): for input row j = 1 (h) the B operand is the 128-row
+// tile starting at W1 ([W1; W0] -> accumulator columns [0,64) and [64,128)), for j = 2 (h+1) the one starting at W2
+// ([W2; W1]); j = 0 uses W0 alone into columns [0,64), j = 3 uses W2 alone into columns [64,128).  Row j = 1 is issued
+// first so that its first MMA initialises both accumulators (the accumulate flag is per instruction).
+// A rows are the same 16-pixel TMA boxes as A_STRIP (14 pixels + halo, horizontal taps = +1024 B descriptor shifts).
+// Warp roles (320 threads): 0-3 epilogue, 4 W producer, 5 MMA issuer + TMEM, 6-9 one input row each.
+#pragma once
+#include "wd_conv_v4.cuh"
+
+namespace wd {
+
+constexpr int kS2Threads = 320;
+constexpr int kS2Stage = 4 * 16384;   // four input rows of 16 pixels x 8 segments x 64 channels
+
+struct Strip2Args {
+    const float* bias;   // [64]
+    int H, W;            // image size (output = input), H even
+    int tiles_w;         // W / 14
+    int num_tiles;       // clips * (H / 2) * tiles_w
+    int relu;
+    int off_w, off_out, off_bar;   // the A ring (two stages) starts at 0
+};
+
+__global__ void __launch_bounds__(kS2Threads, 1)
+conv_strip2_kernel(const __grid_constant__ CUtensorMap wmap,     // [64, 576], box {64, 64}
+                   const __grid_constant__ CUtensorMap amap,     // {C, 8, W, H, clips}, box {64, 8, 16, 1, 1}
+                   const __grid_constant__ CUtensorMap omap,     // [rows, 64], box {64, 32}
+                   const __grid_constant__ CUtensorMap omap16,   // box {64, 16}
+                   const Strip2Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + a.off_w;
+    uint8_t* sOut = smem + a.off_out;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+    uint64_t* a_full = bars;               // [2]
+    uint64_t* a_empty = bars + 2;          // [2]
+    uint64_t* tmem_full_bar = bars + 4;    // [2]
+    uint64_t* tmem_empty_bar = bars + 6;   // [2]
+    uint64_t* w_bar = bars + 8;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    float* sBias = reinterpret_cast<float*>(bars + 16);   // 64 floats
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const int H2 = a.H >> 1;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&wmap);
+            tma_prefetch_desc(&amap);
+            tma_prefetch_desc(&omap);
+            tma_prefetch_desc(&omap16);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&a_full[s], 4);
+                mbar_init(&a_empty[s], 1);
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            mbar_init(w_bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_ptr, 256);   // two buffers of 2 x 64 accumulator columns
+        tmem_relinquish();
+    }
+    if (warp < 4 && tid < 64) sBias[tid] = a.bias[tid];
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
+
+    if (warp < 4) {
+        // ============================== epilogue: two output rows (chunks) per tile ==============================
+        uint8_t* my_out = sOut + warp * kEpiSlab;   // one slab per warp (the shared-memory budget is spent on A and W)
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        const bool relu = a.relu != 0;
+        float4 bb[16];
+        const float4* bsrc = reinterpret_cast<const float4*>(sBias);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int ws = tile % a.tiles_w;
+            const int q = tile / a.tiles_w;
+            const int h = (q % H2) * 2;
+            const int n = q / H2;
+            const int acc = tile_iter & 1;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * 128;
+            mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * 64, v0);
+                tmem_ld32(taddr + c * 64 + 32, v1);
+                tmem_ld_wait();
+                if (c == 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                    __syncwarp();
+                }
+                if (elect_one()) tma_store_wait_read();   // the previous store has finished reading the slab
+                __syncwarp();
+                uint8_t* obuf = my_out + row_off;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t* v = (u < 4) ? (v0 + u * 8) : (v1 + (u - 4) * 8);
+                    const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    uint32_t o[4];
+                    if (relu) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2_relu(f[2 * k], f[2 * k + 1]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    const int mrow = (((n * a.H + h + c) * a.W) + ws * kStripPixels) * 8 + warp * 32;
+                    if (warp == 3) tma_store_2d(&omap16, my_out, 0, mrow);   // 112-row strips: the last warp stores 16 rows
+                    else tma_store_2d(&omap, my_out, 0, mrow);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp == 4) {
+        // ============================== W producer: nine taps, resident, as [s][W2 | W1 | W0] ==============================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(w_bar, 9 * 8192);
+            for (int r = 0; r < 3; ++r)
+                for (int s = 0; s < 3; ++s)
+                    tma_load_2d(&wmap, w_bar, sW + (s * 3 + (2 - r)) * 8192, (r * 3 + s) * kTileK, 0);
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ============================== MMA issuer ==============================
+        constexpr uint32_t idesc64 = umma_idesc_bf16(kTileM, 64);
+        constexpr uint32_t idesc128 = umma_idesc_bf16(kTileM, 128);
+        const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
+        const uint32_t sW_lo = umma_desc_lo(smem_u32(sW));
+        mbar_wait(w_bar, 0);
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int acc = tile_iter & 1, slot = tile_iter & 1;
+            mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+            mbar_wait(&a_full[slot], (tile_iter >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t d0 = tmem_base + acc * 128;
+            const uint32_t a_lo = sA_lo + ((uint32_t)(slot * kS2Stage) >> 4);
+            if (elect_one()) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = jj == 0 ? 1 : (jj == 1 ? 2 : (jj == 2 ? 0 : 3));   // row h first: it initialises both accumulators
+                    // B tile start inside [W2 | W1 | W0] and width / destination of this row's MMAs
+                    const int wsel = (j == 0) ? 2 : (j == 1 ? 1 : 0);
+                    const bool wide = (j == 1 || j == 2);
+                    const uint32_t d = d0 + (j == 3 ? 64u : 0u);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const uint64_t adesc = umma_desc_from_lo(a_lo + (uint32_t)((j * 16384 + s * 1024) >> 4));
+                        const uint64_t bdesc = umma_desc_from_lo(sW_lo + (uint32_t)(((s * 3 + wsel) * 8192) >> 4));
+#pragma unroll
+                        for (int k = 0; k < kTileK / 16; ++k)
+                            umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, wide ? idesc128 : idesc64,
+                                         (jj | s | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&a_empty[slot]);
+                umma_commit(&tmem_full_bar[acc]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================== A producers: warp 6 + j loads input row h - 1 + j ==============================
+        const int j = warp - 6;
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int ws = tile % a.tiles_w;
+            const int q = tile / a.tiles_w;
+            const int h = (q % H2) * 2;
+            const int n = q / H2;
+            const int slot = tile_iter & 1;
+            mbar_wait(&a_empty[slot], ((tile_iter >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&a_full[slot], 16384);
+                tma_load_5d(&amap, &a_full[slot], sA + slot * kS2Stage + j * 16384, 0, 0, ws * kStripPixels - 1, h - 1 + j, n);
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace wd

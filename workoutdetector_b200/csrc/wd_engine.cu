@@ -23,6 +23,7 @@
 #include "wd_stem_pool.cuh"
 #include "wd_tdn_kernels.cuh"
 #include "wd_conv_fuse2.cuh"
+#include "wd_conv_strip2.cuh"
 
 namespace {
 
@@ -980,7 +981,35 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     return WD_OK;
 }
 
+int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 1;  // two output rows per tile for the 64 -> 64 3x3 convolutions
+
+// 3x3 stride 1, 64 -> 64 channels (layer-1 conv2): two output rows per tile, N = 128 MMAs for the shared input rows
+int launch_strip2(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(wd::conv_strip2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Strip2Args p{};
+    p.bias = a.bias;
+    p.H = a.Hout;
+    p.W = a.Wout;
+    p.tiles_w = a.Wout / wd::kStripPixels;
+    p.num_tiles = (a.M / (a.Hout * a.Wout * 8)) * (a.Hout / 2) * p.tiles_w;
+    p.relu = a.relu;
+    p.off_w = 2 * wd::kS2Stage;
+    p.off_out = p.off_w + 9 * 8192;
+    p.off_bar = p.off_out + 4 * wd::kEpiSlab;
+    const size_t smem = (size_t)p.off_bar + 2048 + 1024;
+    const unsigned grid = (unsigned)std::min(p.num_tiles, sm_count);
+    WD_CUDA(launch_pdl(wd::conv_strip2_kernel, grid, (unsigned)wd::kS2Threads, smem, st, c.wmap, c.amap, c.omap, c.omap16, p));
+    return WD_OK;
+}
+
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    if (g_strip2 && c.a_mode == wd::A_STRIP && c.tile_n == 64 && c.Cin == 64 && c.Cout == 64 && a.residual == nullptr &&
+        a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
+        return launch_strip2(c, a, sm_count, st);
     if (eligible_2cta(c, a)) return launch_2cta(c, a, sm_count, st);
     if (g_2cta >= 5 && c.a_mode == wd::A_STRIP && a.residual == nullptr && c.tile_n == 64)
         return launch_2cta_strip<64>(c, a, sm_count, st);  // narrow tiles on a CTA pair: 256 x 64 per instruction
