@@ -1222,8 +1222,10 @@ int make_amap(CUtensorMap* map, const void* base, int Cin, size_t pixels) {
 // column dimension has a 16-byte stride (2 pixels), coordinate c+1 for conv column c (wd_stem_pool.cuh).
 int launch_stem_pool(wd_engine* e, const ConvLayer& c, const void* frames, void* out, int n_clips, cudaStream_t st) {
     static bool configured = false;
+    static const int stem2 = getenv("WD_STEM2") ? atoi(getenv("WD_STEM2")) : 1;  // two conv rows per MMA group
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(wd::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::kSpSmem));
+        WD_CUDA(cudaFuncSetAttribute(wd::stem_pool2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wd::kSpSmem));
         configured = true;
     }
     const uint64_t row = (uint64_t)wd::kFramePitch * 8, frame = 224 * row;
@@ -1240,7 +1242,10 @@ int launch_stem_pool(wd_engine* e, const ConvLayer& c, const void* frames, void*
     p.seg_rows = e->stem_seg_rows;
     p.num_units = n_clips * (56 / p.seg_rows) * 8;
     const int grid = std::min(p.num_units, e->sm_count);
-    WD_CUDA(launch_pdl(wd::stem_pool_kernel, (unsigned)grid, 192u, (size_t)wd::kSpSmem, st, amap, c.wmap, p));
+    if (stem2)
+        WD_CUDA(launch_pdl(wd::stem_pool2_kernel, (unsigned)grid, (unsigned)wd::kSp2Threads, (size_t)wd::kSpSmem, st, amap, c.wmap, p));
+    else
+        WD_CUDA(launch_pdl(wd::stem_pool_kernel, (unsigned)grid, 192u, (size_t)wd::kSpSmem, st, amap, c.wmap, p));
     return WD_OK;
 }
 
