@@ -108,6 +108,12 @@ int wd_pack_nchw_f32(wd_engine* e, const float* x_nchw, int n_frames, void* out_
  * tsn.py:337-338), already normalised.  Differences are formed in fp32 before anything is rounded to bf16. */
 size_t wd_engine_clip_bytes(const wd_engine* e);
 int wd_pack_tdn_f32(wd_engine* e, const float* x, int n_clips, void* out_clips, void* stream);
+/* The same from device uint8 frames: every clip is 40 frames (8 segments x 5 frames, segment-major) picked by src_index
+ * (40 * n_clips entries, or NULL when frames_hwc holds exactly those frames in order; entry < 0 = all-zero raw frame),
+ * each resized / cropped / normalised like wd_preprocess_u8 (datasets/build.py:131-136) in fp32 before the differences
+ * are taken. */
+int wd_preprocess_tdn_u8(wd_engine* e, const uint8_t* frames_hwc, int n_src, int H, int W, const int32_t* src_index,
+                         int n_clips, float in_scale, void* out_clips, void* stream);
 
 /* Replaces TSM.forward (tsm.py:409-419) + to_softmax (utils/visualize.py:140-150) + the arg-max / threshold of
  * utils/eval.py:159-164.

@@ -105,6 +105,32 @@ def test_pack_tdn_layout(tdn_engines, tdn_ref, mode):
     assert err <= (1e-6 if mode == "fp32" else 2 ** -8 * float(ref.abs().max())), err
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_preprocess_tdn_u8_equals_pack_of_oracle_transform(tdn_engines, mode):
+    """uint8 front end: 40 frames per clip through the fp32 resize / normalise pass, then the packers == pack_tdn applied
+    to the oracle's build_test_transform restatement of the same frames (6 clips: two scratch chunks; with a window
+    table containing a zero frame, and at a non-square size)."""
+    from oracle import tsm_oracle as O
+    from workoutdetector_b200.utils.synth import synth_clips_u8
+    e = tdn_engines(mode, max_clips=6)
+    u8 = synth_clips_u8(30, 3)                                   # 240 frames = 6 clips x 40
+    x = O.preprocess_u8(u8).view(6, 8, 5, 3, 224, 224)
+    want = e.pack_tdn(x.cuda())
+    got = e.preprocess_tdn_u8(u8.cuda())
+    torch.cuda.synchronize()
+    tol = 3e-6 if mode == "fp32" else 2 ** -8
+    assert float((got.float() - want.float()).abs().max()) <= tol * max(1.0, float(want.float().abs().max()))
+    g = torch.Generator().manual_seed(4)
+    vid = torch.randint(0, 256, (50, 180, 320, 3), generator=g, dtype=torch.uint8)
+    idx = torch.randint(-1, 50, (80,), generator=g, dtype=torch.int32)
+    zero = torch.zeros(1, 180, 320, 3, dtype=torch.uint8)
+    frames = torch.cat([vid[j:j + 1] if j >= 0 else zero for j in idx.tolist()])
+    want = e.pack_tdn(O.preprocess_u8(frames).view(2, 8, 5, 3, 224, 224).cuda())
+    got = e.preprocess_tdn_u8(vid.cuda(), idx)
+    torch.cuda.synchronize()
+    assert float((got.float() - want.float()).abs().max()) <= tol * max(1.0, float(want.float().abs().max()))
+
+
 def test_tdn_fp32_validation_mode(tdn_engines, tdn_ref, tdn_gold):
     """fp32 mode: every op against the oracle's reference arithmetic; logits / softmax against the REFERENCE module's
     golden output within 1e-4."""

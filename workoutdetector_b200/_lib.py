@@ -57,6 +57,7 @@ SYMBOLS = {
     "wd_pack_nchw_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
     "wd_engine_clip_bytes": (C.c_size_t, [_vp]),
     "wd_pack_tdn_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "wd_preprocess_tdn_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp]),
     "wd_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _i, _vp]),
     "wd_forward_timed": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "wd_count_reps": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

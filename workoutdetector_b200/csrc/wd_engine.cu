@@ -203,6 +203,7 @@ struct wd_engine {
     size_t h_u8_cap = 0;
     int h_chunk = 0;
     uint64_t h_idx = 0;  // chunks submitted through the host entry points (staging slot = h_idx & 1)
+    float* tdn_scratch = nullptr;  // fp32 frames of a few clips (wd_preprocess_tdn_u8)
 };
 
 namespace {
@@ -1606,6 +1607,7 @@ int wd_engine_destroy(wd_engine* e) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->hevent[i]) cudaEventDestroy(e->hevent[i]);
     }
+    if (e->tdn_scratch) cudaFree(e->tdn_scratch);
     if (e->h_logits) cudaFree(e->h_logits);
     if (e->h_probs) cudaFree(e->h_probs);
     if (e->h_state) cudaFree(e->h_state);
@@ -1916,27 +1918,64 @@ size_t wd_engine_clip_bytes(const wd_engine* e) {
     return b;
 }
 
-int wd_pack_tdn_f32(wd_engine* e, const float* x, int n_clips, void* out, void* stream) {
-    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
-    if (e->desc.arch != WD_ARCH_TDN_R50) return fail(WD_ERR_INVALID, "wd_pack_tdn_f32 needs a TDN engine");
-    if (n_clips == 0) return WD_OK;
-    if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
+// centre frames -> `centre`, pooled differences -> `diff` (the two regions of a TDN clip buffer)
+static int tdn_pack(wd_engine* e, const wd::TdnIn& in, int n_clips, void* centre, void* diff, cudaStream_t st) {
     const bool bf = e->desc.mode == WD_MODE_BF16;
     const int pitch = bf ? wd::kFramePitch : 224, pad = bf ? wd::kFramePad : 0;
     const int S = n_clips * 8;
     const size_t total = (size_t)S * 224 * pitch, total_d = (size_t)S * 112 * 112;
     const unsigned grid = (unsigned)((total + 255) / 256), grid_d = (unsigned)((total_d + 255) / 256);
-    void* diff = static_cast<uint8_t*>(out) + (size_t)S * wd_engine_frame_bytes(e);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!bf) {
-        wd::tdn_pack_center_kernel<float><<<grid, 256, 0, st>>>(x, static_cast<float*>(out), S, pitch, pad);
-        wd::tdn_pack_diff_kernel<float><<<grid_d, 256, 0, st>>>(x, static_cast<float*>(diff), S);
+        wd::tdn_pack_center_kernel<float><<<grid, 256, 0, st>>>(in, static_cast<float*>(centre), S, pitch, pad);
+        wd::tdn_pack_diff_kernel<float><<<grid_d, 256, 0, st>>>(in, static_cast<float*>(diff), S);
     } else {
-        wd::tdn_pack_center_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), S, pitch, pad);
-        wd::tdn_pack_diff_kernel<__nv_bfloat16><<<grid_d, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(diff), S);
+        wd::tdn_pack_center_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(centre), S, pitch, pad);
+        wd::tdn_pack_diff_kernel<__nv_bfloat16><<<grid_d, 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(diff), S);
     }
     WD_CUDA(cudaGetLastError());
     e->launches += 2;
+    return WD_OK;
+}
+
+int wd_pack_tdn_f32(wd_engine* e, const float* x, int n_clips, void* out, void* stream) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (e->desc.arch != WD_ARCH_TDN_R50) return fail(WD_ERR_INVALID, "wd_pack_tdn_f32 needs a TDN engine");
+    if (n_clips == 0) return WD_OK;
+    if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
+    const wd::TdnIn in{x, (size_t)3 * 224 * 224, 224 * 224, 224, 1};
+    void* diff = static_cast<uint8_t*>(out) + (size_t)n_clips * 8 * wd_engine_frame_bytes(e);
+    return tdn_pack(e, in, n_clips, out, diff, static_cast<cudaStream_t>(stream));
+}
+
+int wd_preprocess_tdn_u8(wd_engine* e, const uint8_t* frames, int n_src, int H, int W, const int32_t* src_index,
+                         int n_clips, float in_scale, void* out, void* stream) {
+    if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    if (e->desc.arch != WD_ARCH_TDN_R50) return fail(WD_ERR_INVALID, "wd_preprocess_tdn_u8 needs a TDN engine");
+    if (n_clips == 0) return WD_OK;
+    if (!frames || !out) return fail(WD_ERR_INVALID, "frames/out must not be NULL");
+    if (!src_index && n_src != n_clips * 40) return fail(WD_ERR_INVALID, "n_src must be 40 * n_clips without src_index");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Resize / normalise the 40 frames of a clip in fp32 (the differences are taken before anything is rounded to bf16),
+    // a few clips at a time through an engine-owned scratch buffer, then the same packers as wd_pack_tdn_f32.
+    const int chunk = 4;
+    const size_t frame_f32 = (size_t)224 * 224 * 4 * sizeof(float);
+    if (!e->tdn_scratch) WD_CUDA(cudaMalloc(&e->tdn_scratch, (size_t)chunk * 40 * frame_f32));
+    const size_t fb = wd_engine_frame_bytes(e);
+    const size_t diff_bytes = (size_t)56 * 56 * 8 * 64 * e->elem_size;
+    uint8_t* centre = static_cast<uint8_t*>(out);
+    uint8_t* diff = centre + (size_t)n_clips * 8 * fb;
+    for (int c0 = 0; c0 < n_clips; c0 += chunk) {
+        const int nc = std::min(chunk, n_clips - c0);
+        if (src_index)
+            WD_TRY(preprocess_impl(WD_MODE_FP32_VALIDATE, frames, n_src, H, W, src_index + (size_t)c0 * 40, nc * 40, in_scale,
+                                   e->tdn_scratch, st));
+        else
+            WD_TRY(preprocess_impl(WD_MODE_FP32_VALIDATE, frames + (size_t)c0 * 40 * H * W * 3, nc * 40, H, W, nullptr,
+                                   nc * 40, in_scale, e->tdn_scratch, st));
+        ++e->launches;
+        const wd::TdnIn in{e->tdn_scratch, (size_t)224 * 224 * 4, 1, 224 * 4, 4};
+        WD_TRY(tdn_pack(e, in, nc, centre + (size_t)c0 * 8 * fb, diff + (size_t)c0 * diff_bytes, st));
+    }
     return WD_OK;
 }
 

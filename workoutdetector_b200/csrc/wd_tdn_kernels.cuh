@@ -17,9 +17,18 @@
 
 namespace wd {
 
-// x [S, 15, 224, 224] fp32 (S segments; planes 6..8 are the centre frame) -> frames [S, 224, pitch, 4]
+// Input addressing of the TDN packers: element (frame f of 5 per segment, colour c, y, x) = in[f*fs + c*cs + y*ys + x*xs].
+//   what the reference module takes, [S, 15, 224, 224] fp32 (tsn.py:337-338):  fs = 3*224*224, cs = 224*224, ys = 224, xs = 1
+//   the fp32 output of the preprocess kernel, [S*5, 224, 224, 4]:              fs = 224*224*4, cs = 1,       ys = 224*4, xs = 4
+struct TdnIn {
+    const float* in;
+    size_t fs;
+    int cs, ys, xs;
+};
+
+// centre frame (index 2 of 5) of every segment -> frames [S, 224, pitch, 4]
 template <typename OutT>
-__global__ void tdn_pack_center_kernel(const float* __restrict__ in, OutT* __restrict__ out, int S, int pitch, int pad) {
+__global__ void tdn_pack_center_kernel(const TdnIn a, OutT* __restrict__ out, int S, int pitch, int pad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)S * 224 * pitch) return;
     const int x = (int)(i % pitch) - pad;
@@ -30,48 +39,44 @@ __global__ void tdn_pack_center_kernel(const float* __restrict__ in, OutT* __res
         Px4<OutT>::store(out + i * 4, 0.0f, 0.0f, 0.0f);
         return;
     }
-    const size_t HW = 224 * 224;
-    const float* b = in + (f * 15 + 6) * HW + (size_t)y * 224 + x;
-    Px4<OutT>::store(out + i * 4, b[0], b[HW], b[2 * HW]);
+    const float* b = a.in + (f * 5 + 2) * a.fs + (size_t)y * a.ys + (size_t)x * a.xs;
+    Px4<OutT>::store(out + i * 4, b[0], b[a.cs], b[2 * a.cs]);
 }
 
-// x [S, 15, 224, 224] fp32 -> d [clip, 56, 56, t, 64]: channel (py*2+px)*16 + ch holds the 2x2-average-pooled
-// difference channel ch (= 3*k + c: frame k+1 minus frame k, colour c; ch 12..15 are zero) at pooled position
+// the four frame differences of a segment -> 2x2 average pool -> d [clip, 56, 56, t, 64]: channel (py*2+px)*16 + ch holds
+// the pooled difference channel ch (= 3*k + c: frame k+1 minus frame k, colour c; ch 12..15 are zero) at pooled position
 // (2Y+py, 2X+px).  With this space-to-depth view the reference's 7x7 / stride-2 / pad-3 convolution over the 112x112
 // pooled differences is a 4x4 / stride-1 convolution over 56x56x64 (taps -2..+1), which the implicit-GEMM kernels take.
 // One thread = one pooled position (16 channels, 32 B bf16); differences are taken in fp32 before any rounding.
 template <typename OutT>
-__global__ void tdn_pack_diff_kernel(const float* __restrict__ in, OutT* __restrict__ out, int S) {
+__global__ void tdn_pack_diff_kernel(const TdnIn a, OutT* __restrict__ out, int S) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)S * 112 * 112) return;
     const int xx = (int)(i % 112);
     const int yy = (int)((i / 112) % 112);
     const size_t s = i / (112 * 112);
-    const size_t HW = 224 * 224;
-    const float* b = in + s * 15 * HW + (size_t)(2 * yy) * 224 + 2 * xx;
+    const float* b = a.in + s * 5 * a.fs + (size_t)(2 * yy) * a.ys + (size_t)(2 * xx) * a.xs;
     float v[16];
 #pragma unroll
     for (int ch = 0; ch < 12; ++ch) {
         // avg_pool2d(x[ch+3] - x[ch]): the difference is formed per pixel first, as the reference does
-        const float2 a0 = *reinterpret_cast<const float2*>(b + (ch + 3) * HW);
-        const float2 a1 = *reinterpret_cast<const float2*>(b + (ch + 3) * HW + 224);
-        const float2 c0 = *reinterpret_cast<const float2*>(b + ch * HW);
-        const float2 c1 = *reinterpret_cast<const float2*>(b + ch * HW + 224);
-        v[ch] = (((a0.x - c0.x) + (a0.y - c0.y)) + ((a1.x - c1.x) + (a1.y - c1.y))) * 0.25f;
+        const float* hi = b + (size_t)(ch / 3 + 1) * a.fs + (ch % 3) * a.cs;
+        const float* lo = b + (size_t)(ch / 3) * a.fs + (ch % 3) * a.cs;
+        v[ch] = (((hi[0] - lo[0]) + (hi[a.xs] - lo[a.xs])) + ((hi[a.ys] - lo[a.ys]) + (hi[a.ys + a.xs] - lo[a.ys + a.xs]))) * 0.25f;
     }
     v[12] = v[13] = v[14] = v[15] = 0.0f;
     const size_t clip = s >> 3;
     const int t = (int)(s & 7);
     const int Y = yy >> 1, X = xx >> 1, q = ((yy & 1) << 1) | (xx & 1);
     OutT* o = out + ((((clip * 56 + Y) * 56 + X) * 8 + t) * 64) + q * 16;
-    float lo[8], hi[8];
+    float l8[8], h8[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        lo[k] = v[k];
-        hi[k] = v[8 + k];
+        l8[k] = v[k];
+        h8[k] = v[8 + k];
     }
-    store8(o, lo);
-    store8(o + 8, hi);
+    store8(o, l8);
+    store8(o + 8, h8);
 }
 
 __device__ __forceinline__ void load2(const __nv_bfloat16* p, float& a, float& b) {

@@ -155,6 +155,27 @@ class Engine:
         check(self.lib.wd_pack_tdn_f32(self.h, _ptr(x), n, _ptr(out), _stream_ptr(self.device)))
         return out
 
+    def preprocess_tdn_u8(self, frames: torch.Tensor, src_index: Optional[torch.Tensor] = None,
+                          in_scale: float = 1.0 / 255.0) -> torch.Tensor:
+        """cuda uint8 [n,H,W,3] -> the TDN clip buffer (as pack_tdn): 40 frames per clip (8 segments x 5 frames) picked by
+        ``src_index`` (or all of ``frames`` in order), resized / normalised like preprocess_u8 in fp32, then centre
+        frames + pooled differences."""
+        assert self.arch == "tdn" and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
+        frames = frames.contiguous()
+        n, H, W, _ = frames.shape
+        if src_index is not None:
+            src_index = src_index.to(self.device, torch.int32).contiguous()
+            n_out = src_index.numel()
+        else:
+            n_out = n
+        assert n_out % 40 == 0
+        nc = n_out // 40
+        esz = 2 if self.mode == MODE_BF16 else 4
+        out = torch.empty((nc * self.clip_bytes // esz,), dtype=self.frame_dtype, device=self.device)
+        check(self.lib.wd_preprocess_tdn_u8(self.h, _ptr(frames), n, H, W, _ptr(src_index), nc, float(in_scale), _ptr(out),
+                                            _stream_ptr(self.device)))
+        return out
+
     def image_view(self, frames: torch.Tensor) -> torch.Tensor:
         """Engine frames -> the [n,224,224,3] image they hold (a view: no zero columns, no padding channel)."""
         return frames[:, :, self.frame_pad:self.frame_pad + 224, :3]
