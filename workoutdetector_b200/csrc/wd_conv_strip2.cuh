@@ -226,3 +226,237 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap wmap,     // [64, 576], b
 }
 
 }  // namespace wd
+
+namespace wd {
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv_strip2s_kernel<BN> — two output rows per tile for the wider 3x3 stride-1 convolutions whose weights do not fit in
+// shared memory (layer 2: 128 -> 128, 28 x 28).  These ran on CTA pairs (conv_2cta_strip_kernel) to halve the W stream,
+// but a cta_group::2 MMA with N = 128 occupies both tensor cores for ~143 cycles, i.e. it is no faster per SM than two
+// single-CTA N = 128 MMAs at the 76-cycle floor would be if the single CTA could afford the W traffic.  With two output
+// rows per tile it can: every tap's W tile (BN x 64, streamed through a ring) is used by two MMA chains — output row h
+// with input row j = r, output row h+1 with input row j = r + 1 — so W traffic per strip halves, and the four input rows
+// of a stage serve both output rows.
+// Warp roles (320 threads): 0-3 epilogue, 4 W producer, 5 MMA issuer + TMEM, 6-9 one input row each.
+// A stages: one per (tile, 64-channel block), two in flight.  TMEM: two buffers of 2 x BN columns.
+// ------------------------------------------------------------------------------------------------------------------
+struct Strip2sArgs {
+    const float* bias;   // [BN]
+    int H, W, tiles_w, num_tiles, relu;
+    int cin_blocks;      // Cin / 64
+    int w_stages;        // W ring depth (taps)
+    int off_w, off_out, off_bar;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kS2Threads, 1)
+conv_strip2s_kernel(const __grid_constant__ CUtensorMap wmap,     // [BN, 9 * Cin], box {64, BN}
+                    const __grid_constant__ CUtensorMap amap,     // {C, 8, W, H, clips}, box {64, 8, 16, 1, 1}
+                    const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
+                    const Strip2sArgs a) {
+    constexpr int kWTile = BN * kTileK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + a.off_w;
+    uint8_t* sOut = smem + a.off_out;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+    uint64_t* a_full = bars;               // [2]
+    uint64_t* a_empty = bars + 2;          // [2]
+    uint64_t* w_full = bars + 4;           // [8]
+    uint64_t* w_empty = bars + 12;         // [8]
+    uint64_t* tmem_full_bar = bars + 20;   // [2]
+    uint64_t* tmem_empty_bar = bars + 22;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
+    float* sBias = reinterpret_cast<float*>(bars + 32);   // BN floats
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const int H2 = a.H >> 1;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&wmap);
+            tma_prefetch_desc(&amap);
+            tma_prefetch_desc(&omap);
+            tma_prefetch_desc(&omap16);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&a_full[s], 4);
+                mbar_init(&a_empty[s], 1);
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(&w_full[s], 1);
+                mbar_init(&w_empty[s], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_ptr, 4 * BN);
+        tmem_relinquish();
+    }
+    if (warp < 4)
+        for (int i = tid; i < BN; i += 128) sBias[i] = a.bias[i];
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
+
+    if (warp < 4) {
+        // ============================== epilogue: 2 output rows x BN / 64 column chunks per tile ==============================
+        uint8_t* my_out = sOut + warp * kEpiSlab;
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        const bool relu = a.relu != 0;
+        constexpr int kChunks = BN / 64;
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int ws = tile % a.tiles_w;
+            const int q = tile / a.tiles_w;
+            const int h = (q % H2) * 2;
+            const int n = q / H2;
+            const int acc = tile_iter & 1;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * 2 * BN;
+            mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int cc = 0; cc < 2 * kChunks; ++cc) {
+                const int c = cc / kChunks, hf = cc % kChunks;   // output row h + c, columns [64 hf, 64 hf + 64)
+                float4 bb[16];
+                const float4* bsrc = reinterpret_cast<const float4*>(sBias + hf * 64);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * BN + hf * 64, v0);
+                tmem_ld32(taddr + c * BN + hf * 64 + 32, v1);
+                tmem_ld_wait();
+                if (cc == 2 * kChunks - 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                    __syncwarp();
+                }
+                if (elect_one()) tma_store_wait_read();
+                __syncwarp();
+                uint8_t* obuf = my_out + row_off;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t* v = (u < 4) ? (v0 + u * 8) : (v1 + (u - 4) * 8);
+                    const float4 b0 = bb[2 * u], b1 = bb[2 * u + 1];
+                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    uint32_t o[4];
+                    if (relu) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2_relu(f[2 * k], f[2 * k + 1]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(obuf + ((u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    const int mrow = (((n * a.H + h + c) * a.W) + ws * kStripPixels) * 8 + warp * 32;
+                    if (warp == 3) tma_store_2d(&omap16, my_out, hf * 64, mrow);
+                    else tma_store_2d(&omap, my_out, hf * 64, mrow);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp == 4) {
+        // ============================== W producer: 9 taps per 64-channel block, through the ring ==============================
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
+            for (int cb = 0; cb < a.cin_blocks; ++cb)
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int slot = it % a.w_stages;
+                    mbar_wait(&w_empty[slot], ((it / a.w_stages) & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&w_full[slot], kWTile);
+                        tma_load_2d(&wmap, &w_full[slot], sW + slot * kWTile, (tap * a.cin_blocks + cb) * kTileK, 0);
+                    }
+                    __syncwarp();
+                }
+    } else if (warp == 5) {
+        // ============================== MMA issuer: every tap feeds both output rows ==============================
+        constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+        const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
+        const uint32_t sW_lo = umma_desc_lo(smem_u32(sW));
+        uint32_t ita = 0, itw = 0;
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int acc = tile_iter & 1;
+            mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d0 = tmem_base + acc * 2 * BN;
+            for (int cb = 0; cb < a.cin_blocks; ++cb, ++ita) {
+                const int aslot = ita & 1;
+                mbar_wait(&a_full[aslot], (ita >> 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * kS2Stage) >> 4);
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap, ++itw) {
+                    const int wslot = itw % a.w_stages;
+                    mbar_wait(&w_full[wslot], (itw / a.w_stages) & 1);
+                    tc_fence_after_sync();
+                    const int r = tap / 3, s = tap - 3 * r;
+                    const uint64_t bdesc = umma_desc_from_lo(sW_lo + ((uint32_t)(wslot * kWTile) >> 4));
+                    const uint64_t adesc0 = umma_desc_from_lo(a_lo + (uint32_t)((r * 16384 + s * 1024) >> 4));         // row h-1+r -> out h
+                    const uint64_t adesc1 = umma_desc_from_lo(a_lo + (uint32_t)(((r + 1) * 16384 + s * 1024) >> 4));   // row h+r   -> out h+1
+                    const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kTileK / 16; ++k) umma_bf16_ss(d0, adesc0 + 2 * k, bdesc + 2 * k, idesc, k ? 1u : first);
+#pragma unroll
+                        for (int k = 0; k < kTileK / 16; ++k) umma_bf16_ss(d0 + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, k ? 1u : first);
+                        umma_commit(&w_empty[wslot]);
+                        if (tap == 8) {
+                            umma_commit(&a_empty[aslot]);
+                            if (cb == a.cin_blocks - 1) umma_commit(&tmem_full_bar[acc]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ============================== A producers: warp 6 + j loads input row h - 1 + j of every (tile, channel block) ==============================
+        const int j = warp - 6;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const int ws = tile % a.tiles_w;
+            const int q = tile / a.tiles_w;
+            const int h = (q % H2) * 2;
+            const int n = q / H2;
+            for (int cb = 0; cb < a.cin_blocks; ++cb, ++it) {
+                const int slot = it & 1;
+                mbar_wait(&a_empty[slot], ((it >> 1) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&a_full[slot], 16384);
+                    tma_load_5d(&amap, &a_full[slot], sA + slot * kS2Stage + j * 16384, cb * kTileK, 0, ws * kStripPixels - 1,
+                                h - 1 + j, n);
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 4 * BN);
+}
+
+}  // namespace wd

@@ -982,7 +982,7 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     return WD_OK;
 }
 
-int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 1;  // two output rows per tile for the 64 -> 64 3x3 convolutions
+int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 1;  // two output rows per tile: 1 = the 64 -> 64 3x3 convolutions, 2 = + the 128-wide ones
 
 // 3x3 stride 1, 64 -> 64 channels (layer-1 conv2): two output rows per tile, N = 128 MMAs for the shared input rows
 int launch_strip2(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
@@ -1007,7 +1007,37 @@ int launch_strip2(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     return WD_OK;
 }
 
+// 3x3 stride 1 with 128 output channels (layer-2 conv2): two output rows per tile, W streamed once per tile pair of rows
+int launch_strip2s(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_strip2s_kernel<128>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Strip2sArgs p{};
+    p.bias = a.bias;
+    p.H = a.Hout;
+    p.W = a.Wout;
+    p.tiles_w = a.Wout / wd::kStripPixels;
+    p.num_tiles = (a.M / (a.Hout * a.Wout * 8)) * (a.Hout / 2) * p.tiles_w;
+    p.relu = a.relu;
+    p.cin_blocks = a.cin_blocks;
+    const int wtile = 128 * 128;
+    p.off_w = 2 * wd::kS2Stage;
+    p.w_stages = std::min(8, (232448 - p.off_w - 4 * wd::kEpiSlab - 2048 - 1024) / wtile);
+    p.off_out = p.off_w + p.w_stages * wtile;
+    p.off_bar = p.off_out + 4 * wd::kEpiSlab;
+    const size_t smem = (size_t)p.off_bar + 2048 + 1024;
+    const unsigned grid = (unsigned)std::min(p.num_tiles, sm_count);
+    WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kS2Threads, smem, st, c.wmap, c.amap, c.omap, c.omap16, p));
+    return WD_OK;
+}
+
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    if (g_strip2 >= 2 && c.a_mode == wd::A_STRIP && c.tile_n == 128 && c.Cout == 128 && a.residual == nullptr &&
+        a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
+        return launch_strip2s(c, a, sm_count, st);
     if (g_strip2 && c.a_mode == wd::A_STRIP && c.tile_n == 64 && c.Cin == 64 && c.Cout == 64 && a.residual == nullptr &&
         a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
         return launch_strip2(c, a, sm_count, st);
