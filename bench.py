@@ -263,7 +263,7 @@ def main():
     # achieved = their algorithmic FLOPs / the sum of their CUDA-event durations; traffic = their summed DRAM bytes.
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["sustained"], traffic=traffic,
-                    kernel=f"the {n_tc} tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), conv_strip2_kernel (layer-1 3x3), conv_fuse2_kernel (layer 1: conv3 + next conv1), stem_pool2_kernel",
+                    kernel=f"the {n_tc} tcgen05 launches of a step, aggregated: conv_2cta_kernel / conv_2cta_strip_kernel (cta_group::2, layers 2-4), conv_v4_kernel (layers 1-2), conv_strip2 / conv_strip2s kernels (layer-1 / layer-2 3x3, two output rows per tile), conv_fuse2_kernel (layer 1: conv3 + next conv1), stem_pool2_kernel",
                     frac_of_burst=achieved / peaks["burst"], peak_source=peaks["source"],
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / max(sum(op_ms), 1e-9),
                     dram_gbs=(traffic / (conv_ms * 1e-3) / 1e9) if traffic else None,

@@ -982,7 +982,7 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     return WD_OK;
 }
 
-int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 1;  // two output rows per tile: 1 = the 64 -> 64 3x3 convolutions, 2 = + the 128-wide ones
+int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 2;  // two output rows per tile: 1 = the 64 -> 64 3x3 convolutions, 2 = + the 128-wide ones
 
 // 3x3 stride 1, 64 -> 64 channels (layer-1 conv2): two output rows per tile, N = 128 MMAs for the shared input rows
 int launch_strip2(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
