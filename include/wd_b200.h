@@ -180,7 +180,8 @@ int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems)
  * at the next wd_engine_load_weights.
  * Environment switches read at wd_engine_create (A/B measurements and differential tests): WD_FUSE_DS (0 / 1 / 2: fold
  * the block-0 downsample into conv3: off / layer 1 / all layers, default 2), WD_FUSE2 (0 / 1 / 2: layer-1 conv3 + the next
- * conv1 in one kernel: off / inside layer 1 / + layer2.0.conv1, default 2), WD_HEAD_SPLIT (0 / 1), WD_HOST_CHUNK. */
+ * conv1 in one kernel: off / inside layer 1 / + layer2.0.conv1, default 2), WD_HEAD_SPLIT (0 / 1), WD_STEM2 (0 / 1: two conv rows per MMA group in the stem), WD_STRIP2 (0..3: two output rows per
+ * tile in the 3x3 convolutions: off / 64-wide / + 128-wide / + the stride-2 one of layer 2, default 3), WD_HOST_CHUNK. */
 int wd_engine_set_option(wd_engine* e, const char* key, int value);
 /* Number of kernels the engine launched since creation (all are this library's own kernels). */
 int64_t wd_engine_launch_count(const wd_engine* e);

@@ -137,6 +137,9 @@ struct ConvLayer {
     CUtensorMap omap16;  // output, box {64, 16}: last warp of a 112-row strip tile
     CUtensorMap wmap_half; // W [Cout, K], box {64, tile_n / 2}: one CTA's half of a W tile (cta_group::2 kernels)
     CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
+    CUtensorMap amap_s2; // stride-2 3x3 (conv_strip2d_kernel): contiguous 16-pixel row boxes of the INPUT {C, T, W, H, clips}
+    CUtensorMap omap24;  // output, box {64, 24}
+    bool has_s2 = false;
 };
 
 // TDN motion excitation + temporal Conv1d of one BottleneckShift (tdn.py:188-334, 339-376); all fp32 on device
@@ -982,7 +985,7 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     return WD_OK;
 }
 
-int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 2;  // two output rows per tile: 1 = the 64 -> 64 3x3 convolutions, 2 = + the 128-wide ones
+int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 3;  // two output rows per tile: 1 = the 64 -> 64 3x3 convolutions, 2 = + the 128-wide ones, 3 = + the stride-2 3x3 of layer 2
 
 // 3x3 stride 1, 64 -> 64 channels (layer-1 conv2): two output rows per tile, N = 128 MMAs for the shared input rows
 int launch_strip2(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
@@ -1034,7 +1037,33 @@ int launch_strip2s(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cuda
     return WD_OK;
 }
 
+// 3x3 stride 2, 128 -> 128 (layer2.0.conv2): contiguous input-row boxes, pixel stride 2 in the MMA descriptor
+int launch_strip2d(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(wd::conv_strip2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Strip2dArgs p{};
+    p.bias = a.bias;
+    p.Hin = a.Hin; p.Win = a.Win; p.Hout = a.Hout; p.Wout = a.Wout;
+    p.num_tiles = (a.M / (a.Hout * a.Wout * 8)) * (a.Hout / 2) * (a.Wout / 7);
+    p.relu = a.relu;
+    p.cin_blocks = a.cin_blocks;
+    const int wtile = 128 * 128;
+    p.off_w = 2 * wd::kS2dStage;
+    p.w_stages = std::min(8, (232448 - p.off_w - 4 * wd::kEpiSlab - 2048 - 1024) / wtile);
+    if (p.w_stages < 2) return fail(WD_ERR_INVALID, "%s: no room for the W ring", c.name.c_str());
+    p.off_out = p.off_w + p.w_stages * wtile;
+    p.off_bar = p.off_out + 4 * wd::kEpiSlab;
+    const size_t smem = (size_t)p.off_bar + 2048 + 1024;
+    const unsigned grid = (unsigned)std::min(p.num_tiles, sm_count);
+    WD_CUDA(launch_pdl(wd::conv_strip2d_kernel, grid, (unsigned)wd::kS2dThreads, smem, st, c.wmap, c.amap_s2, c.omap, c.omap24, p));
+    return WD_OK;
+}
+
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    if (g_strip2 >= 3 && c.has_s2 && a.residual == nullptr && c.kb_split == 0) return launch_strip2d(c, a, sm_count, st);
     if (g_strip2 >= 2 && c.a_mode == wd::A_STRIP && c.tile_n == 128 && c.Cout == 128 && a.residual == nullptr &&
         a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
         return launch_strip2s(c, a, sm_count, st);
@@ -1812,6 +1841,12 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                                          d.stride, c.Wout == 7 ? 7 : wd::kStripPixels));
                     c.rmap = c.amap32;  // the CTA-pair kernel takes the second A map in its (unused) residual slot
                 }
+            }
+            if (c.k == 3 && c.stride == 2 && c.Cin == 128 && c.Cout == 128 && c.tile_n == 128 && c.Wout % 7 == 0 &&
+                c.Hout % 2 == 0 && o.in_buf >= 0 && o.res_buf < 0) {   // layer2.0.conv2: row boxes + stride in the descriptor
+                WD_TRY(make_amap5(&c.amap_s2, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
+                WD_TRY(make_omap(&c.omap24, e->buf[o.out_buf], c.Cout, rows, 24));
+                c.has_s2 = true;
             }
             if (c.a_mode != wd::A_TMA) continue;
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
