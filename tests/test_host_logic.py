@@ -224,3 +224,22 @@ def test_tdn_module_state_dict_layout_matches_reference():
         m2(torch.zeros(40, 3, 224, 224))
     with pytest.raises(NotImplementedError):
         tdn.create_model(num_class=3, num_segments=16)
+
+
+def test_engine_session_rejects_foreign_models_and_reports_shapes():
+    """serving.EngineSession wraps only this package's engine-backed modules; its get_inputs()/get_outputs() describe the
+    ORT surface the reference's callers expect (utils/inference_count.py:265-276)."""
+    from workoutdetector_b200.models import create_model
+    from workoutdetector_b200.models import tdn
+    from workoutdetector_b200.serving import EngineSession
+    with pytest.raises(TypeError):
+        EngineSession(torch.nn.Linear(2, 2))
+    s = EngineSession(create_model(num_class=11, device="cpu"), softmax=True)
+    assert s.get_inputs()[0].name == "input" and s.get_inputs()[0].shape == ["N", 8, 3, 224, 224]
+    assert s.get_outputs()[0].shape == ["N", 11]
+    with pytest.raises(KeyError):
+        s.run(None, {"x": np.zeros((1, 8, 3, 224, 224), np.float32)})
+    with pytest.raises(RuntimeError, match="CUDA"):      # no CPU path behind the session either
+        s.run(None, {"input": np.zeros((1, 8, 3, 224, 224), np.float32)})
+    t = EngineSession(tdn.create_model(num_class=3))
+    assert t.get_inputs()[0].shape == ["N", 8, 5, 3, 224, 224]
