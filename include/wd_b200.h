@@ -139,6 +139,14 @@ int wd_forward_timed(wd_engine* e, const void* frames, int n_clips, float* logit
 int wd_count_reps(const int32_t* states, const int32_t* lens, int V, int Wmax, int step, int32_t* counts,
                   int32_t* reps, int reps_stride, int32_t* reps_len, void* stream);
 
+/* Replaces the 7-frame majority vote of count_by_image_model (utils/inference_count.py:211-231): a deque of the last
+ * `window` per-frame arg-max labels, state = (sum(deque) >= votes); the reference uses window 7, votes 4 and then
+ * pred_to_count(step = 7) (wd_count_reps).
+ *   labels : device int32 [V, Fmax] per-frame arg-max class   lens : device int32 [V] or NULL (all Fmax)
+ *   states : device int32 [V, Fmax]: 0 / 1; entries past lens[v] are written as -1 (skipped by the counter) */
+int wd_vote_states(const int32_t* labels, const int32_t* lens, int V, int Fmax, int window, int votes,
+                   int32_t* states, void* stream);
+
 /* Replaces to_softmax (utils/visualize.py:140-150) + the arg-max / threshold loop of utils/eval.py:153-164 for
  * score arrays that already exist (score JSONs): scores device fp32 [rows, classes] -> probs (nullable) and
  * state int32 [rows] with the same rule as wd_forward. */
@@ -154,10 +162,9 @@ int wd_infer_u8_host(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, 
                      int32_t* host_state);
 
 /* Streaming form of wd_infer_u8_host for callers that feed batch after batch (a video stream, a dataset pass): the
- * call enqueues H2D copy -> preprocess -> forward -> D2H and returns; up to two batches are in flight, so the copy of
- * batch i+1 overlaps the compute of batch i.  host_frames_hwc and the three output arrays must be PINNED host memory
- * and stay untouched until wd_infer_host_sync (or until two later calls have been issued and synchronised, for the
- * inputs).  Results of a call are complete after wd_infer_host_sync returns. */
+ * call enqueues H2D copy -> preprocess -> forward -> D2H and returns; up to three batches are in flight (three staging
+ * slots fenced by per-slot events), so the copies of the next batches overlap the compute of this one.  host_frames_hwc
+ * and the three output arrays must be PINNED host memory and stay untouched until wd_infer_host_sync.  Results of a call are complete after wd_infer_host_sync returns. */
 int wd_infer_u8_host_async(wd_engine* e, const uint8_t* host_frames_hwc, int n_clips, int H, int W, float in_scale,
                            float threshold, int apply_softmax, float* host_logits, float* host_probs,
                            int32_t* host_state);
@@ -176,8 +183,10 @@ int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems)
  * 2 v3, 3 v4 = default), "use_strip" (0/1: row-strip A operand for 3x3 stride-1 convolutions, v3/v4),
  * "stem_seg_rows" (pooled rows per work unit of the fused stem, divides 56), "use_2cta" (CTA-pair kernels: 0 off,
  * 1 1x1 conv1, 2 + 3x3 strips, 3 + tap boxes, 4 + residual conv3 = default, 5 + narrow N = 64 strips (slower, kept for
- * measurements)), "pdl" (0/1 programmatic dependent launch), "prefetch_kblocks" (-1 = per-layer rule).  Takes effect
- * at the next wd_engine_load_weights.
+ * measurements)), "pdl" (0/1 programmatic dependent launch), "prefetch_kblocks" (-1 = per-layer rule).  All are
+ * per-engine.  "pdl", "prefetch_kblocks" and "stem_seg_rows" act on the next forward; the others change the op plan or
+ * the packed weight layout: setting one to a new value invalidates the uploaded weights (wd_forward returns
+ * WD_ERR_STATE) until wd_engine_load_weights has run again.
  * Environment switches read at wd_engine_create (A/B measurements and differential tests): WD_FUSE_DS (0 / 1 / 2: fold
  * the block-0 downsample into conv3: off / layer 1 / all layers, default 2), WD_FUSE2 (0 / 1 / 2: layer-1 conv3 + the next
  * conv1 in one kernel: off / inside layer 1 / + layer2.0.conv1, default 2), WD_HEAD_SPLIT (0 / 1), WD_STEM2 (0 / 1: two conv rows per MMA group in the stem), WD_STRIP2 (0..3: two output rows per

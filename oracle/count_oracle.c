@@ -33,3 +33,23 @@ int oracle_count_reps(const int32_t* states, const int32_t* lens, int V, int Wma
     }
     return 0;
 }
+
+/* The 7-frame majority vote of count_by_image_model (utils/inference_count.py:213-224), same array signature as
+ * wd_vote_states: states[v][f] = (sum of labels[v][max(0, f-window+1) .. f] >= votes), -1 past lens[v]. */
+int oracle_vote_states(const int32_t* labels, const int32_t* lens, int V, int Fmax, int window, int votes,
+                       int32_t* states) {
+    for (int v = 0; v < V; ++v) {
+        int len = lens ? lens[v] : Fmax;
+        if (len > Fmax) len = Fmax;
+        for (int f = 0; f < Fmax; ++f) {
+            if (f >= len) {
+                states[(int64_t)v * Fmax + f] = -1;
+                continue;
+            }
+            int sum = 0;
+            for (int j = f - window + 1 < 0 ? 0 : f - window + 1; j <= f; ++j) sum += labels[(int64_t)v * Fmax + j];
+            states[(int64_t)v * Fmax + f] = sum >= votes ? 1 : 0;
+        }
+    }
+    return 0;
+}

@@ -4,7 +4,9 @@ Pure-Python restatement of ``pred_to_count`` (workoutdetector/utils/inference_co
 metrics (utils/eval.py:11-24 ``obo_mae``; datasets/repcount_dataset.py:212-251 ``RepcountHelper.eval_count``).
 Pinned by the reference's own known-answer vectors (tests/test_inference_count.py:8-48, the doctest at
 inference_count.py:140-143) in tests/test_oracle_golden.py, and by outputs of the reference function itself on
-random state sequences (tests/golden/count_vectors.json, written by oracle/gen_golden.py).
+random state sequences (tests/golden/count_vectors.json, written by oracle/gen_golden.py).  ``vote_states`` restates
+the 7-frame vote of count_by_image_model (inference_count.py:213-224); pinned by tests/golden/image_vote.json, which
+oracle/gen_golden.py writes by running the reference's own count_by_image_model loop on seeded per-frame scores.
 """
 from typing import List, Sequence, Tuple
 
@@ -29,6 +31,22 @@ def pred_to_count(preds: Sequence[int], step: int) -> Tuple[int, List[int]]:
         if pred != preds[start_idx]:                     # :160-162 (preds[start_idx] may be -1 at the start)
             start_idx = idx
     return count, reps
+
+
+def vote_states(labels: Sequence[int], window: int = 7, votes: int = 4) -> List[int]:
+    """The majority vote of count_by_image_model (utils/inference_count.py:213-224): a deque(maxlen=window) of the
+    per-frame arg-max labels; state = sum(deque) >= votes (a bool there; 0 / 1 here — pred_to_count treats them alike)."""
+    out: List[int] = []
+    for f in range(len(labels)):
+        out.append(1 if sum(labels[max(0, f - window + 1):f + 1]) >= votes else 0)   # :222-224
+    return out
+
+
+def count_by_image_labels(labels: Sequence[int]) -> Tuple[int, List[int], List[int]]:
+    """Labels -> vote (window 7, votes 4) -> pred_to_count(step=7) (utils/inference_count.py:213-235)."""
+    st = vote_states(labels, 7, 4)
+    c, r = pred_to_count(st, 7)
+    return c, r, st
 
 
 def obo_mae(preds: Sequence[int], targets: Sequence[int]) -> Tuple[float, float]:

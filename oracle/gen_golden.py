@@ -12,6 +12,10 @@ runs the reference functions on seeded inputs, asserts that oracle/*.py reproduc
   tests/golden/eval_golden.json     obo_mae / RepcountHelper.eval_count / to_softmax outputs of the reference
   tests/golden/tdn_golden.npz       logits + hooked activations of the reference TDN module (tdn.create_model) for a
                                     seeded state_dict and seeded [B,8,5,3,224,224] inputs
+  tests/golden/image_vote.json      count_by_image_model's own loop (deque vote + pred_to_count(step=7)) on seeded
+                                    per-frame scores (cv2 / inference_image replaced by stand-ins)
+  tests/golden/pre_downscale.npz    build_test_transform(False) with Resize(256, antialias=False) on down-scaling
+                                    geometries (360x640, 272x480, 300x206, 240x320) + 224x224
 
 Usage:  python oracle/gen_golden.py            (from the repo root)
 """
@@ -340,6 +344,94 @@ def gen_eval(ref_eval, ref_vis, ref_ds, out):
     print(f"eval: obo_mae / to_softmax / RepcountHelper.eval_count pinned; split sizes {res['split_sizes']}")
 
 
+def gen_image_vote(ref_ic, out):
+    """count_by_image_model (utils/inference_count.py:192-243) run literally: cv2.VideoCapture and inference_image of
+    the reference module are replaced by seeded stand-ins (F dummy frames, seeded per-frame scores), everything from
+    the deque vote to pred_to_count(step=7) is the reference's own code."""
+    from oracle import count_oracle as CO
+    rng = np.random.RandomState(21)
+    cases = []
+
+    class FakeCap:
+        def __init__(self, n):
+            self.n, self.i = n, 0
+
+        def read(self):
+            self.i += 1
+            return (self.i <= self.n), np.zeros((4, 4, 3), np.uint8)
+
+        def release(self):
+            pass
+
+        def isOpened(self):
+            return True
+
+    for i in range(300):
+        F = int(rng.choice([0, 1, 3, 6, 7, 8, 20, 57, 130, 400]))
+        C = int(rng.choice([2, 2, 2, 3, 5]))
+        # sticky per-frame label process with flicker, turned into scores whose arg-max is the label (ties included)
+        lab, cur, stick = [], int(rng.randint(0, C)), rng.uniform(0.7, 0.97)
+        for _ in range(F):
+            if rng.rand() > stick:
+                cur = int(rng.randint(0, C))
+            lab.append(cur if rng.rand() > 0.1 else int(rng.randint(0, C)))
+        scores = []
+        for l in lab:
+            sc = np.round(rng.rand(C) * 4) / 8.0          # coarse values -> exact ties happen
+            sc[l] = sc.max() + (0.0 if rng.rand() < 0.3 else 0.25)   # 30 %: the label ties with the maximum
+            scores.append(sc.astype(np.float32))
+        it = iter(scores)
+        with mock.patch.object(ref_ic.cv2, "VideoCapture", lambda path, n=F: FakeCap(n)), \
+                mock.patch.object(ref_ic, "inference_image", lambda model, frame: next(it)), \
+                mock.patch("builtins.print"):
+            count, reps = ref_ic.count_by_image_model(None, f"case{i}.mp4", ground_truth=None)
+        labels = [int(np.argmax(sc)) for sc in scores]
+        c2, r2, st = CO.count_by_image_labels(labels)
+        assert (c2, r2) == (count, reps), (i, count, c2)
+        cases.append(dict(name=f"vote{i}", scores=[[float(x) for x in sc] for sc in scores], labels=labels, states=st,
+                          count=count, reps=reps))
+    with open(out, "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print(f"image vote: {len(cases)} videos through the reference's count_by_image_model loop, oracle == reference; "
+          f"total reps {sum(c['count'] for c in cases)}")
+
+
+def gen_pre_downscale(ref_build, out):
+    """build_test_transform(person_crop=False) of the reference on DOWN-scaling geometries with
+    T.Resize(256, antialias=False) — the pinned torchvision 0.13 tensor behaviour that oracle/tsm_oracle.py restates
+    (torchvision 0.26, which this image has, would antialias by default)."""
+    import functools
+    from oracle import tsm_oracle as O
+    T = ref_build.T
+    orig = T.Resize
+    arrays = {}
+    rows = np.array(sorted(set(range(0, 224, 8)) | {1, 222, 223}))
+    arrays["rows"] = rows
+    from oracle.synth import synth_frames_u8
+    try:
+        T.Resize = functools.partial(orig, antialias=False)
+        t = ref_build.build_test_transform(person_crop=False)
+    finally:
+        T.Resize = orig
+    for H, W in ((360, 640), (272, 480), (300, 206), (224, 224), (240, 320)):
+        u8 = synth_frames_u8(2, H, W, 5)                               # regenerated by the tests from the same seed
+        y = t(u8.permute(0, 3, 1, 2))                                  # the reference transform (uint8 NCHW input)
+        yo = O.preprocess_u8(u8)
+        d = float((y - yo).abs().max())
+        assert d < 2e-6, (H, W, d)
+        yq = t(u8.permute(0, 3, 1, 2).float())                         # float-promotion quirk: no /255
+        yqo = O.preprocess_u8(u8, in_scale=1.0)
+        dq = float((yq - yqo).abs().max())
+        assert dq < 1e-3, (H, W, dq)
+        arrays[f"u8sum_{H}x{W}"] = np.array([int(u8.to(torch.int64).sum())])
+        arrays[f"out_{H}x{W}"] = y[:, :, rows][:, :, :, rows].numpy().copy()
+        arrays[f"quirk_{H}x{W}"] = yq[:, :, rows][:, :, :, rows].numpy().copy()
+        print(f"preprocess {H}x{W}: oracle vs reference transform (Resize antialias=False) max abs diff {d:.3g} "
+              f"(quirk path {dq:.3g})")
+    np.savez_compressed(out, **arrays)
+    print(f"wrote {out} ({os.path.getsize(out) / 1024:.0f} KiB)")
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("gen_golden.py needs /root/reference (build container only)")
@@ -352,6 +444,10 @@ def main():
     ref_vis = importlib.import_module("workoutdetector.utils.visualize")
     ref_ds = importlib.import_module("workoutdetector.datasets.repcount_dataset")
     torch.set_num_threads(os.cpu_count())
+    if "--r2-only" in sys.argv:   # the fixtures added in round 2 (the round-1 files stay byte-identical)
+        gen_image_vote(ref_ic, os.path.join(GOLD, "image_vote.json"))
+        gen_pre_downscale(ref_build, os.path.join(GOLD, "pre_downscale.npz"))
+        return
     if "--tdn-only" in sys.argv:
         gen_tdn(importlib.import_module("workoutdetector.models.tdn"), os.path.join(GOLD, "tdn_golden.npz"))
         return
@@ -366,6 +462,8 @@ def main():
     arrays.update(extra)
     np.savez_compressed(npz, **arrays)
     gen_tdn(importlib.import_module("workoutdetector.models.tdn"), os.path.join(GOLD, "tdn_golden.npz"))
+    gen_image_vote(ref_ic, os.path.join(GOLD, "image_vote.json"))
+    gen_pre_downscale(ref_build, os.path.join(GOLD, "pre_downscale.npz"))
 
 
 if __name__ == "__main__":

@@ -15,7 +15,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0",   # 0 = one optimisation thread per host core
 ]
 
 
@@ -62,6 +62,7 @@ SYMBOLS = {
     "wd_forward_timed": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "wd_count_reps": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "wd_scores_to_states": (_i, [_vp, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "wd_vote_states": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "wd_infer_u8_host": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
     "wd_infer_u8_host_async": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
     "wd_infer_host_sync": (_i, [_vp]),

@@ -217,8 +217,10 @@ __global__ void __launch_bounds__(256) preprocess_u8_rows_kernel(const PreArgs a
         *reinterpret_cast<uint4*>(srow + (size_t)v * 16) = val;
     }
     __syncthreads();
-    // one thread = one output column for all kPreRows rows: the horizontal taps are computed once per thread, the
-    // vertical ones are warp-uniform
+    // one thread = one output column for all kPreRows rows.  The horizontal blend of a source row is computed once and
+    // reused by every output row that touches it (up-scaling 224 -> 256: 8 output rows share 8-9 source rows, so 9
+    // instead of 16 blends); the vertical taps are warp-uniform, so the reuse tests are uniform branches.
+    // uint8 -> float without the quarter-rate I2F: PRMT the byte under the exponent of 2^23 and subtract 2^23 (exact).
     const int col = threadIdx.x;
     if (col >= a.pitch) return;
     const int ox = col - a.pad;
@@ -233,29 +235,66 @@ __global__ void __launch_bounds__(256) preprocess_u8_rows_kernel(const PreArgs a
     const int x0 = min((int)sx, a.W - 1);
     const int x1 = min(x0 + 1, a.W - 1);
     const float lx = sx - (float)x0;
-    const uint8_t* c0 = srow + shift + x0 * 3;
-    const uint8_t* c1 = srow + shift + x1 * 3;
+    const uint32_t off_c0 = (uint32_t)(shift + x0 * 3), off_c1 = (uint32_t)(shift + x1 * 3);
+    const uint32_t row_b = (uint32_t)row_bytes;
+    const float in_scale = a.in_scale;
+    auto load3 = [&](uint32_t byte_off, float (&v)[3]) {   // three consecutive bytes at any alignment: two words + funnel shift
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(srow) + (byte_off >> 2);
+        const uint32_t x = __funnelshift_r(w[0], w[1], (byte_off & 3u) * 8u);
+        v[0] = (__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650)) - 8388608.0f) * in_scale;
+        v[1] = (__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7651)) - 8388608.0f) * in_scale;
+        v[2] = (__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7652)) - 8388608.0f) * in_scale;
+    };
+    auto hrow = [&](int y, float (&h)[3]) {                 // horizontal blend of source row y at this column
+        float v0[3], v1[3];
+        const uint32_t ro = (uint32_t)(y - ya) * row_b;
+        load3(ro + off_c0, v0);
+        load3(ro + off_c1, v1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h[c] = v0[c] * (1.0f - lx) + v1[c] * lx;   // same association as ATen's upsample_bilinear2d
+    };
     const float rstd[3] = {1.0f / a.stdv[0], 1.0f / a.stdv[1], 1.0f / a.stdv[2]};
-#pragma unroll 4
+    int py0 = -1, py1 = -1;
+    float ptop[3] = {0.f, 0.f, 0.f}, pbot[3] = {0.f, 0.f, 0.f};
+#pragma unroll
     for (int r = 0; r < kPreRows; ++r) {
         int y0, y1;
         float ly;
         src_y(oy0 + r, y0, y1, ly);
-        const size_t off0 = (size_t)(y0 - ya) * row_bytes, off1 = (size_t)(y1 - ya) * row_bytes;
+        float top[3], bot[3];
+        if (y0 == py0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) top[c] = ptop[c];
+        } else if (y0 == py1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) top[c] = pbot[c];
+        } else {
+            hrow(y0, top);
+        }
+        if (y1 == y0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bot[c] = top[c];
+        } else if (y1 == py1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bot[c] = pbot[c];
+        } else if (y1 == py0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bot[c] = ptop[c];
+        } else {
+            hrow(y1, bot);
+        }
         float res[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float v00 = (float)c0[off0 + c] * a.in_scale;
-            const float v01 = (float)c1[off0 + c] * a.in_scale;
-            const float v10 = (float)c0[off1 + c] * a.in_scale;
-            const float v11 = (float)c1[off1 + c] * a.in_scale;
-            const float top = v00 * (1.0f - lx) + v01 * lx;   // same association as preprocess_u8_kernel / ATen
-            const float bot = v10 * (1.0f - lx) + v11 * lx;
-            const float v = top * (1.0f - ly) + bot * ly;
+            const float v = top[c] * (1.0f - ly) + bot[c] * ly;
             // fp32 (validation mode) divides like torchvision's Normalize; bf16 multiplies by 1/std (<= 1.5 fp32 ulp
             // before the bf16 rounding, three IEEE divisions per pixel were a third of this kernel's instructions)
             res[c] = sizeof(OutT) == 4 ? (v - a.mean[c]) / a.stdv[c] : (v - a.mean[c]) * rstd[c];
+            ptop[c] = top[c];
+            pbot[c] = bot[c];
         }
+        py0 = y0;
+        py1 = y1;
         Px4<OutT>::store(o + (size_t)r * a.pitch * 4, res[0], res[1], res[2]);
     }
 }
@@ -618,6 +657,29 @@ __global__ void count_reps_kernel(const int32_t* __restrict__ states, const int3
         counts[v] = count;
         if (reps_len) reps_len[v] = 2 * count;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Majority vote of the image-model counting path — reference: workoutdetector/utils/inference_count.py:211-231
+// (count_by_image_model): a deque of the last `window` (7) per-frame arg-max labels, state = (sum(deque) >= votes (4)).
+// One thread per (video, frame); the window is clipped at the start of the video exactly like a filling deque.
+//   labels [V, Fmax] int32, lens [V] or NULL; states [V, Fmax] int32 (0 / 1; frames past lens[v] are written as -1,
+//   which the counter skips)
+// ------------------------------------------------------------------------------------------------
+__global__ void vote_states_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ lens, int V, int Fmax,
+                                   int window, int votes, int32_t* __restrict__ states) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)V * Fmax) return;
+    const int v = (int)(i / Fmax), f = (int)(i % Fmax);
+    const int len = lens ? min(lens[v], Fmax) : Fmax;
+    if (f >= len) {
+        states[i] = -1;
+        return;
+    }
+    const int32_t* row = labels + (size_t)v * Fmax;
+    int sum = 0;
+    for (int j = max(0, f - window + 1); j <= f; ++j) sum += __ldg(row + j);
+    states[i] = sum >= votes ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,6 +35,7 @@ __device__ __forceinline__ void tma_store_wait_read1() {
 
 constexpr int kEpiSlab = 32 * 128;  // one warp's 32 rows x 64 bf16 columns
 
+#ifdef WD_LEGACY_KERNELS  // second generation (persistent): differential-test builds only
 template <int BN, int STAGES>
 struct PersistSmem {
     static constexpr int kBTileBytes = BN * kTileK * 2;
@@ -330,5 +331,6 @@ conv_umma_persistent(const __grid_constant__ CUtensorMap wmap, const __grid_cons
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
 }
+#endif  // WD_LEGACY_KERNELS
 
 }  // namespace wd

@@ -47,6 +47,7 @@ struct ConvArgs {
     int num_tiles;  // m_tiles * n_tiles (persistent kernel)
 };
 
+#ifdef WD_LEGACY_KERNELS  // first generation (one tile per CTA): differential-test builds only, not in the product library
 template <int BN, int STAGES>
 struct ConvSmem {
     static constexpr int kBTileBytes = BN * kTileK * 2;
@@ -272,5 +273,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, BN);
 }
+#endif  // WD_LEGACY_KERNELS
 
 }  // namespace wd

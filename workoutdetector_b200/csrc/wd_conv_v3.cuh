@@ -47,6 +47,7 @@ struct ConvArgs3 {
     uint32_t* trace;       // v4 debug: CTA 0 writes clock() samples of its pipeline roles here (nullable)
 };
 
+#ifdef WD_LEGACY_KERNELS  // third generation (W-resident, strip 3x3): differential-test builds only
 template <int BN, int AMODE>
 __global__ void __launch_bounds__((AMODE == A_TMA || AMODE == A_STRIP) ? 224 : 320, 1)
 conv_v3_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap,
@@ -411,5 +412,6 @@ conv_v3_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
 }
+#endif  // WD_LEGACY_KERNELS
 
 }  // namespace wd

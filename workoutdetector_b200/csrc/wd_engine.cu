@@ -44,6 +44,31 @@ int fail(int code, const char* fmt, ...) {
             return fail(WD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+// Makes `device` current for the scope of one C-ABI call and restores the caller's device afterwards (PyTorch reads the
+// process-wide current device; an engine on cuda:1 must not change it as a side effect).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// Device that owns a device pointer (-1 if the runtime cannot tell): entry points without an engine run there.
+int device_of(const void* p) {
+    cudaPointerAttributes at{};
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+}
+
 #define WD_TRY(expr)            \
     do {                        \
         int _r = (expr);        \
@@ -105,6 +130,7 @@ inline uint16_t f32_to_bf16_bits(float f) {  // round-to-nearest-even, as __floa
 // ---------------------------------------------------------------------------------------------------
 enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_MAXPOOL = 2, OP_HEAD = 3, OP_STEMPOOL = 4, OP_BLEND = 5, OP_MSE = 6 };
 constexpr int kMaxBufs = 8;
+constexpr int kHostSlots = 3;  // staging slots of the host entry points: up to three batches in flight
 constexpr int kInDiff = -2;  // Op::in_buf: the difference tensor that follows the centre frames in a TDN input buffer
 
 struct ConvLayer {
@@ -178,6 +204,9 @@ struct wd_engine {
     int fuse_ds_requested = 2;  // WD_FUSE_DS at create time
     int fuse2 = 1;              // layer-1 conv3 + next conv1 in one kernel (needs fuse_ds >= 1 and 256-wide tiles)
     int fuse2_requested = 1;    // WD_FUSE2 at create time
+    int use_2cta = 4;          // per-engine copies of the launch-helper switches (set_option "use_2cta" / "pdl" /
+    int pdl = 1;               // "prefetch_kblocks"); run_forward installs them before launching
+    int prefetch_kblocks = -1;
     int stem_seg_rows = 28;  // pooled rows per work unit of the fused stem + max-pool kernel
     int sm_count = 148;
     std::vector<ConvLayer> convs;
@@ -196,16 +225,17 @@ struct wd_engine {
     int64_t tap_cap = 0;
     int64_t launches = 0;
     // host-call staging (wd_infer_u8_host)
-    cudaStream_t hstream[2] = {nullptr, nullptr};
-    cudaEvent_t hevent[2] = {nullptr, nullptr};
-    uint8_t* h_u8[2] = {nullptr, nullptr};
-    void* h_frames[2] = {nullptr, nullptr};
+    cudaStream_t hstream[2] = {nullptr, nullptr};   // [0] compute, [1] copies + preprocess
+    cudaEvent_t hevent[kHostSlots] = {};    // compute that read slot i has finished
+    cudaEvent_t hcopied[kHostSlots] = {};   // slot i holds preprocessed frames
+    uint8_t* h_u8[kHostSlots] = {};
+    void* h_frames[kHostSlots] = {};
     float* h_logits = nullptr;
     float* h_probs = nullptr;
     int32_t* h_state = nullptr;
     size_t h_u8_cap = 0;
     int h_chunk = 0;
-    uint64_t h_idx = 0;  // chunks submitted through the host entry points (staging slot = h_idx & 1)
+    uint64_t h_idx = 0;  // chunks submitted through the host entry points (staging slot = h_idx % kHostSlots)
     float* tdn_scratch = nullptr;  // fp32 frames of a few clips (wd_preprocess_tdn_u8)
 };
 
@@ -637,6 +667,7 @@ cudaError_t launch_pdl_grid(void (*kernel)(KArgs...), dim3 grid, unsigned block,
 }
 int g_head_split = getenv("WD_HEAD_SPLIT") ? atoi(getenv("WD_HEAD_SPLIT")) : 1;  // 4 CTAs per clip in the head
 
+#ifdef WD_LEGACY_KERNELS
 template <int BN, int STAGES, int AMODE>
 int launch_conv_t(const CUtensorMap& wmap, const CUtensorMap& amap, const wd::ConvArgs& a, cudaStream_t st) {
     using L = wd::ConvSmem<BN, STAGES>;
@@ -688,6 +719,8 @@ int launch_persist(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cuda
     return fail(WD_ERR_INVALID, "no persistent conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
 }
 
+#endif  // WD_LEGACY_KERNELS
+
 // Shared-memory plan of conv_v3_kernel for one layer (see wd_conv_v3.cuh).
 struct SmemPlan {
     int a_stages, b_stages, w_resident, a_stage_bytes, off_b, off_out, off_res, off_bar, total;
@@ -726,6 +759,7 @@ int plan_smem(int BN, int mode, int kblocks, bool has_res, bool grid_keeps_n_til
     return WD_OK;
 }
 
+#ifdef WD_LEGACY_KERNELS
 template <int BN, int AMODE>
 int launch_v3_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
@@ -780,6 +814,7 @@ int launch_v3(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
     }
     return fail(WD_ERR_INVALID, "no v3 conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
 }
+#endif  // WD_LEGACY_KERNELS
 
 
 uint32_t* g_trace = nullptr;  // debug timeline buffer (WD_TRACE=<file> with the single-layer hooks)
@@ -1089,6 +1124,7 @@ int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
 
 int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st);
 
+#ifdef WD_LEGACY_KERNELS
 int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
     const int mode = c.a_mode;
     switch (c.tile_n) {
@@ -1107,16 +1143,22 @@ int launch_conv(const ConvLayer& c, const wd::ConvArgs& a, cudaStream_t st) {
     }
     return fail(WD_ERR_INVALID, "no conv kernel for tile_n=%d a_mode=%d", c.tile_n, mode);
 }
+#endif  // WD_LEGACY_KERNELS
 
 int launch_any(const ConvLayer& c, const wd::ConvArgs& a, int version, int sm_count, cudaStream_t st) {
     if (version >= 3) return launch_v4(c, a, sm_count, st);
     if (c.kb_split > 0)
         return fail(WD_ERR_INVALID, "%s runs with the downsample fused into its K dimension: needs the v4 kernel "
                     "(create the engine with WD_FUSE_DS=0 to use older generations)", c.name.c_str());
+#ifdef WD_LEGACY_KERNELS
     if (version == 2) return launch_v3(c, a, sm_count, st);
     if (c.a_mode == wd::A_STRIP) return fail(WD_ERR_INVALID, "strip mode needs the v3/v4 kernel");
     if (version == 1) return launch_persist(c, a, sm_count, st);
     return launch_conv(c, a, st);
+#else
+    return fail(WD_ERR_UNSUPPORTED, "conv kernel generation %d is not in this build: the product library carries the v4 / "
+                "CTA-pair kernels only (compile with -DWD_LEGACY_KERNELS for the older generations)", version);
+#endif
 }
 
 wd::ConvArgs conv_args(const ConvLayer& c, const void* in, void* out, const void* res, int clips) {
@@ -1401,6 +1443,10 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
         return fail(WD_ERR_INVALID, "n_clips=%d outside [0, max_clips=%d]", n_clips, e->desc.max_clips);
     if (n_clips == 0) return WD_OK;
     if (!frames || !logits) return fail(WD_ERR_INVALID, "frames/logits must not be NULL");
+    DeviceGuard guard(e->desc.device);
+    g_2cta = e->use_2cta;   // the launch helpers read these; they are per-engine settings (wd_engine_set_option)
+    g_pdl = e->pdl;
+    g_prefetch_kblocks = e->prefetch_kblocks;
     const bool f32 = e->desc.mode == WD_MODE_FP32_VALIDATE;
     std::vector<cudaEvent_t> ev;
     if (op_ms) {
@@ -1574,7 +1620,7 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     a.pad = f32 ? 0 : wd::kFramePad;
     // rows of the source a band of kPreRows output rows can touch (+2 for the bilinear neighbour and rounding)
     const size_t band_rows = (size_t)std::ceil(wd::kPreRows * a.scale_y) + 2;
-    const size_t smem_rows = band_rows * W * 3 + 48;
+    const size_t smem_rows = band_rows * W * 3 + 64;  // + alignment shift, 16-byte rounding and the word over-read
     if (smem_rows <= 40 * 1024) {
         dim3 grid(224 / wd::kPreRows, n_out);
         if (f32)
@@ -1613,7 +1659,10 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     if (d->arch == WD_ARCH_TSM_R50 && d->is_shift && (d->shift_div < 1 || 64 % d->shift_div != 0 || (64 / d->shift_div) % 8 != 0))
         return fail(WD_ERR_INVALID, "shift_div=%d: fold must be a multiple of 8 channels", d->shift_div);
     if (d->mode != WD_MODE_BF16 && d->mode != WD_MODE_FP32_VALIDATE) return fail(WD_ERR_INVALID, "bad mode");
-    WD_CUDA(cudaSetDevice(d->device));
+    int ndev = 0;
+    WD_CUDA(cudaGetDeviceCount(&ndev));
+    if (d->device < 0 || d->device >= ndev) return fail(WD_ERR_INVALID, "device %d out of range (%d visible)", d->device, ndev);
+    DeviceGuard guard(d->device);
     cudaDeviceProp prop;
     WD_CUDA(cudaGetDeviceProperties(&prop, d->device));
     if (prop.major != 10)
@@ -1623,6 +1672,9 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->desc = *d;
     e->sm_count = prop.multiProcessorCount;
     e->elem_size = d->mode == WD_MODE_FP32_VALIDATE ? 4 : 2;
+    e->use_2cta = getenv("WD_2CTA") ? atoi(getenv("WD_2CTA")) : 4;
+    e->pdl = getenv("WD_PDL") ? atoi(getenv("WD_PDL")) : 1;
+    e->prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETCH_KBLOCKS")) : -1;
     e->fuse_ds_requested = getenv("WD_FUSE_DS") ? atoi(getenv("WD_FUSE_DS")) : 2;  // 0 off, 1 layer1.0, 2 + the stride-2 blocks
     e->fuse_ds = e->fuse_ds_requested;
     e->fuse2_requested = getenv("WD_FUSE2") ? atoi(getenv("WD_FUSE2")) : 2;  // 1: inside layer 1, 2: + layer2.0.conv1
@@ -1646,7 +1698,7 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
 
 int wd_engine_destroy(wd_engine* e) {
     if (!e) return WD_OK;
-    cudaSetDevice(e->desc.device);
+    DeviceGuard guard(e->desc.device);
     for (auto& c : e->convs) {
         if (c.w_packed) cudaFree(c.w_packed);
         if (c.bias) cudaFree(c.bias);
@@ -1660,12 +1712,14 @@ int wd_engine_destroy(wd_engine* e) {
     if (e->head_ticket) cudaFree(e->head_ticket);
     if (e->fc_w) cudaFree(e->fc_w);
     if (e->fc_b) cudaFree(e->fc_b);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kHostSlots; ++i) {
         if (e->h_u8[i]) cudaFree(e->h_u8[i]);
         if (e->h_frames[i]) cudaFree(e->h_frames[i]);
-        if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->hevent[i]) cudaEventDestroy(e->hevent[i]);
+        if (e->hcopied[i]) cudaEventDestroy(e->hcopied[i]);
     }
+    for (int i = 0; i < 2; ++i)
+        if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
     if (e->tdn_scratch) cudaFree(e->tdn_scratch);
     if (e->h_logits) cudaFree(e->h_logits);
     if (e->h_probs) cudaFree(e->h_probs);
@@ -1676,26 +1730,33 @@ int wd_engine_destroy(wd_engine* e) {
 
 int wd_engine_set_option(wd_engine* e, const char* key, int value) {
     if (!e || !key) return fail(WD_ERR_INVALID, "engine/key NULL");
+    // Options that change the op plan or the packed weight layout invalidate the uploaded weights: wd_forward fails
+    // with WD_ERR_STATE until wd_engine_load_weights has run again.
     if (!strcmp(key, "use_tma_a")) {
+        if (e->use_tma_a != (value ? 1 : 0)) e->weights_loaded = false;
         e->use_tma_a = value ? 1 : 0;
     } else if (!strcmp(key, "persistent")) {
         if (value < 0 || value > 3) return fail(WD_ERR_INVALID, "persistent must be 0..3");
+        if (e->persistent != value) e->weights_loaded = false;
         e->persistent = value;
     } else if (!strcmp(key, "use_2cta")) {
         if (value < 0 || value > 5) return fail(WD_ERR_INVALID, "use_2cta must be 0..5");
-        g_2cta = value;
+        if (e->use_2cta != value) e->weights_loaded = false;   // the A-operand mode of 7-pixel rows depends on it
+        e->use_2cta = value;
     } else if (!strcmp(key, "pdl")) {
-        g_pdl = value ? 1 : 0;
+        e->pdl = value ? 1 : 0;
     } else if (!strcmp(key, "prefetch_kblocks")) {
         if (value < -1 || value > 256) return fail(WD_ERR_INVALID, "prefetch_kblocks must be in [-1, 256]");
-        g_prefetch_kblocks = value;
+        e->prefetch_kblocks = value;
     } else if (!strcmp(key, "stem_seg_rows")) {
         if (value < 1 || 56 % value != 0) return fail(WD_ERR_INVALID, "stem_seg_rows must divide 56");
         e->stem_seg_rows = value;
     } else if (!strcmp(key, "use_strip")) {
+        if (e->use_strip != (value ? 1 : 0)) e->weights_loaded = false;
         e->use_strip = value ? 1 : 0;
     } else if (!strcmp(key, "tile_n_max")) {
         if (value != 64 && value != 128 && value != 256) return fail(WD_ERR_INVALID, "tile_n_max must be 64/128/256");
+        if (e->tile_n_max != value) e->weights_loaded = false;
         e->tile_n_max = value;
     } else {
         return fail(WD_ERR_INVALID, "unknown option '%s'", key);
@@ -1705,7 +1766,8 @@ int wd_engine_set_option(wd_engine* e, const char* key, int value) {
 
 int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     if (!e || (!t && n > 0)) return fail(WD_ERR_INVALID, "engine/tensors NULL");
-    WD_CUDA(cudaSetDevice(e->desc.device));
+    DeviceGuard guard(e->desc.device);
+    e->weights_loaded = false;   // set again only when every tensor has been folded, packed and uploaded
     std::map<std::string, const wd_named_tensor*> m;
     for (int i = 0; i < n; ++i)
         if (t[i].name && t[i].data) m[t[i].name] = &t[i];
@@ -1740,6 +1802,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             WD_TRY(e->desc.arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e));
         }
     }
+    g_2cta = e->use_2cta;   // upload_conv's A-operand mode decision reads it
     std::map<int, std::vector<float>> folded_w, folded_shift;
     for (ConvLayer& c : e->convs) {
         const int64_t wn = c.s2d ? (int64_t)c.Cout * 12 * 49 : (int64_t)c.Cout * c.Cin * c.k * c.k;
@@ -1952,6 +2015,7 @@ int wd_engine_frame_geometry(const wd_engine* e, int32_t* height, int32_t* pitch
 int wd_preprocess_u8(wd_engine* e, const uint8_t* frames, int n_src, int H, int W, const int32_t* src_index,
                      int n_out, float in_scale, void* out, void* stream) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
+    DeviceGuard guard(e->desc.device);
     WD_TRY(preprocess_impl(e->desc.mode, frames, n_src, H, W, src_index, n_out, in_scale, out,
                            static_cast<cudaStream_t>(stream)));
     if (n_out > 0) ++e->launches;
@@ -1962,6 +2026,7 @@ int wd_pack_nchw_f32(wd_engine* e, const float* x, int n_frames, void* out, void
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
     if (n_frames == 0) return WD_OK;
     if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
+    DeviceGuard guard(e->desc.device);
     const bool bf = e->desc.mode == WD_MODE_BF16;
     const int pitch = bf ? wd::kFramePitch : 224, pad = bf ? wd::kFramePad : 0;
     const size_t total = (size_t)n_frames * 224 * pitch;
@@ -2007,6 +2072,7 @@ int wd_pack_tdn_f32(wd_engine* e, const float* x, int n_clips, void* out, void* 
     if (e->desc.arch != WD_ARCH_TDN_R50) return fail(WD_ERR_INVALID, "wd_pack_tdn_f32 needs a TDN engine");
     if (n_clips == 0) return WD_OK;
     if (!x || !out) return fail(WD_ERR_INVALID, "x/out must not be NULL");
+    DeviceGuard guard(e->desc.device);
     const wd::TdnIn in{x, (size_t)3 * 224 * 224, 224 * 224, 224, 1};
     void* diff = static_cast<uint8_t*>(out) + (size_t)n_clips * 8 * wd_engine_frame_bytes(e);
     return tdn_pack(e, in, n_clips, out, diff, static_cast<cudaStream_t>(stream));
@@ -2019,6 +2085,7 @@ int wd_preprocess_tdn_u8(wd_engine* e, const uint8_t* frames, int n_src, int H, 
     if (n_clips == 0) return WD_OK;
     if (!frames || !out) return fail(WD_ERR_INVALID, "frames/out must not be NULL");
     if (!src_index && n_src != n_clips * 40) return fail(WD_ERR_INVALID, "n_src must be 40 * n_clips without src_index");
+    DeviceGuard guard(e->desc.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // Resize / normalise the 40 frames of a clip in fp32 (the differences are taken before anything is rounded to bf16),
     // a few clips at a time through an engine-owned scratch buffer, then the same packers as wd_pack_tdn_f32.
@@ -2062,6 +2129,8 @@ int wd_count_reps(const int32_t* states, const int32_t* lens, int V, int Wmax, i
     if (V < 0 || Wmax < 0) return fail(WD_ERR_INVALID, "negative V/Wmax");
     if (V == 0) return WD_OK;
     if (!counts || (Wmax > 0 && !states)) return fail(WD_ERR_INVALID, "states/counts must not be NULL");
+    const int dev = device_of(counts);
+    DeviceGuard guard(dev >= 0 ? dev : 0);
     const int threads = 128;  // 4 videos per block
     const unsigned grid = (unsigned)(((size_t)V * 32 + threads - 1) / threads);
     wd::count_reps_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(states, lens, V, Wmax, step, counts,
@@ -2075,10 +2144,27 @@ int wd_scores_to_states(const float* scores, int rows, int classes, float thresh
     if (rows < 0 || classes < 1) return fail(WD_ERR_INVALID, "bad rows/classes");
     if (rows == 0) return WD_OK;
     if (!scores || !state) return fail(WD_ERR_INVALID, "scores/state must not be NULL");
+    const int dev = device_of(state);
+    DeviceGuard guard(dev >= 0 ? dev : 0);
     const int threads = 128;
     const unsigned grid = (unsigned)(((size_t)rows * 32 + threads - 1) / threads);
     wd::scores_to_states_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         scores, rows, classes, threshold, apply_softmax, probs, state);
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int wd_vote_states(const int32_t* labels, const int32_t* lens, int V, int Fmax, int window, int votes,
+                   int32_t* states, void* stream) {
+    if (V < 0 || Fmax < 0) return fail(WD_ERR_INVALID, "negative V/Fmax");
+    if (window < 1) return fail(WD_ERR_INVALID, "window must be >= 1");
+    if (V == 0 || Fmax == 0) return WD_OK;
+    if (!labels || !states) return fail(WD_ERR_INVALID, "labels/states must not be NULL");
+    const int dev = device_of(states);
+    DeviceGuard guard(dev >= 0 ? dev : 0);
+    const size_t total = (size_t)V * Fmax;
+    wd::vote_states_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        labels, lens, V, Fmax, window, votes, states);
     WD_CUDA(cudaGetLastError());
     return WD_OK;
 }
@@ -2092,7 +2178,7 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
     if (n_clips == 0) return WD_OK;
     if (!host || !host_logits) return fail(WD_ERR_INVALID, "host_frames/host_logits must not be NULL");
     if (n_clips > e->desc.max_clips) return fail(WD_ERR_INVALID, "n_clips=%d > max_clips=%d", n_clips, e->desc.max_clips);
-    WD_CUDA(cudaSetDevice(e->desc.device));
+    DeviceGuard guard(e->desc.device);
     // Chunk schedule.  Synchronous call: a small first chunk (its H2D copy is the only one nothing can hide) and then
     // chunks as large as the staging buffers allow, so that the convolutions run at large-batch efficiency while the
     // next copy streams over PCIe.  Asynchronous call: the copy hides behind the previous call's compute, so the whole
@@ -2103,9 +2189,10 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
     const size_t clip_bytes = (size_t)8 * H * W * 3;
     const int C = e->desc.num_class;
     if (!e->hstream[0]) {
-        for (int i = 0; i < 2; ++i) {
-            WD_CUDA(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) WD_CUDA(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kHostSlots; ++i) {
             WD_CUDA(cudaEventCreateWithFlags(&e->hevent[i], cudaEventDisableTiming));
+            WD_CUDA(cudaEventCreateWithFlags(&e->hcopied[i], cudaEventDisableTiming));
             WD_CUDA(cudaMalloc(&e->h_frames[i], (size_t)chunk * 8 * wd_engine_frame_bytes(e)));
         }
         WD_CUDA(cudaMalloc(&e->h_logits, (size_t)e->desc.max_clips * C * sizeof(float)));
@@ -2116,7 +2203,7 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
     if (e->h_u8_cap < (size_t)chunk * clip_bytes) {
         WD_CUDA(cudaStreamSynchronize(e->hstream[0]));
         WD_CUDA(cudaStreamSynchronize(e->hstream[1]));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostSlots; ++i) {
             if (e->h_u8[i]) cudaFree(e->h_u8[i]);
             e->h_u8[i] = nullptr;
             WD_CUDA(cudaMalloc(&e->h_u8[i], (size_t)chunk * clip_bytes));
@@ -2124,8 +2211,8 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
         e->h_u8_cap = (size_t)chunk * clip_bytes;
         e->h_idx = 0;
     }
-    // Copies run on hstream[1]; compute for every chunk runs on hstream[0] because the workspace is shared.  The two
-    // staging slots alternate across chunks AND across calls (h_idx persists); reuse is fenced with events.
+    // Copies run on hstream[1]; compute for every chunk runs on hstream[0] because the workspace is shared.  The
+    // staging slots rotate across chunks AND across calls (h_idx persists); reuse is fenced with per-slot events.
     cudaStream_t cs = e->hstream[0];
     cudaStream_t cp = e->hstream[1];
     int done = 0;
@@ -2133,9 +2220,9 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
     while (done < n_clips) {
         const int nc = std::min(first ? first_chunk : chunk, n_clips - done);
         first = false;
-        const int slot = (int)(e->h_idx & 1);
+        const int slot = (int)(e->h_idx % kHostSlots);
         // wait until the compute that last used this slot has finished before overwriting its staging buffer
-        if (e->h_idx >= 2) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
+        if (e->h_idx >= (uint64_t)kHostSlots) WD_CUDA(cudaStreamWaitEvent(cp, e->hevent[slot], 0));
         WD_CUDA(cudaMemcpyAsync(e->h_u8[slot], host + (size_t)done * clip_bytes, (size_t)nc * clip_bytes,
                                 cudaMemcpyHostToDevice, cp));
         // resize / normalise on the copy stream as well: it overlaps the previous chunk's convolutions (its CTAs fit
@@ -2143,11 +2230,8 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
         WD_TRY(preprocess_impl(e->desc.mode, e->h_u8[slot], nc * 8, H, W, nullptr, nc * 8, in_scale,
                                e->h_frames[slot], cp));
         ++e->launches;
-        cudaEvent_t copied;
-        WD_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-        WD_CUDA(cudaEventRecord(copied, cp));
-        WD_CUDA(cudaStreamWaitEvent(cs, copied, 0));
-        WD_CUDA(cudaEventDestroy(copied));
+        WD_CUDA(cudaEventRecord(e->hcopied[slot], cp));
+        WD_CUDA(cudaStreamWaitEvent(cs, e->hcopied[slot], 0));
         WD_TRY(run_forward(e, e->h_frames[slot], nc, e->h_logits + (size_t)done * C, e->h_probs + (size_t)done * C,
                            e->h_state + done, threshold, apply_softmax, cs, nullptr));
         WD_CUDA(cudaEventRecord(e->hevent[slot], cs));
@@ -2181,7 +2265,7 @@ int wd_infer_u8_host_async(wd_engine* e, const uint8_t* host, int n_clips, int H
 int wd_infer_host_sync(wd_engine* e) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
     if (!e->hstream[0]) return WD_OK;
-    WD_CUDA(cudaSetDevice(e->desc.device));
+    DeviceGuard guard(e->desc.device);
     WD_CUDA(cudaStreamSynchronize(e->hstream[0]));
     WD_CUDA(cudaStreamSynchronize(e->hstream[1]));
     return WD_OK;

@@ -74,22 +74,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// Spin on try_wait (which itself sleeps in hardware for a bounded time). A wait that never completes is a
-// protocol bug; with WD_BOUNDED_WAIT (default) it traps after ~seconds instead of hanging the GPU.
+// Spin on try_wait (which itself sleeps in hardware for a bounded time).  A wait that never completes is a protocol bug.
+// WD_BOUNDED_WAIT (default 1) bounds it by WALL TIME (%globaltimer, WD_WAIT_TIMEOUT_NS, default 20 s) — not by a poll
+// count, which a profiler replay, a sanitizer, a debugger or GPU time-slicing can exceed on a healthy kernel (early
+// PDL-launched CTAs legitimately spin while the previous grid finishes).  After the bound the kernel traps, so a
+// protocol bug surfaces as a CUDA error instead of a hung GPU.  The timer is read only every 4096 failed polls.
 #ifndef WD_BOUNDED_WAIT
 #define WD_BOUNDED_WAIT 1
 #endif
-// Debug aid (WD_DEBUG_WAIT=1 with the single-layer hooks): instead of trapping, a wait that does not complete records
-// {blockIdx, warp, barrier smem address, parity} and gives up, so the kernel ends and the host can print the record.
+#ifndef WD_WAIT_TIMEOUT_NS
+#define WD_WAIT_TIMEOUT_NS 20000000000ull
+#endif
+// Debug aid (WD_DEBUG_WAIT=1 with the single-layer hooks): instead of trapping, a wait that does not complete within
+// 2^20 polls records {blockIdx, warp, barrier smem address, parity} and gives up, so the kernel ends and the host
+// prints the record; g_wd_wait_dbg_n != 0 afterwards means the kernel's output is invalid (the hook reports it).
 __device__ uint32_t g_wd_wait_dbg[4 * 64];
 __device__ uint32_t g_wd_wait_dbg_n;
 __device__ int g_wd_wait_nofatal;
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if WD_BOUNDED_WAIT
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (g_wd_wait_nofatal ? (1u << 20) : (1u << 26))) {
-            if (!g_wd_wait_nofatal) __trap();
+        if ((++spins & 4095u) != 0) continue;
+        if (g_wd_wait_nofatal) {
+            if (spins < (1u << 20)) continue;
             if ((threadIdx.x & 31) == 0) {
                 const uint32_t i = atomicAdd(&g_wd_wait_dbg_n, 1u);
                 if (i < 64) {
@@ -101,6 +115,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             }
             return;
         }
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > WD_WAIT_TIMEOUT_NS) __trap();
     }
 #else
     while (!mbar_try_wait(bar, parity)) {

@@ -116,20 +116,27 @@ class Engine:
         return t
 
     def preprocess_u8(self, frames: torch.Tensor, src_index: Optional[torch.Tensor] = None,
-                      in_scale: float = 1.0 / 255.0) -> torch.Tensor:
+                      in_scale: float = 1.0 / 255.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """frames: cuda uint8 [n,H,W,3] -> engine frames [n_out, *frame_shape] (datasets/build.py:131-136 semantics);
-        image_view() strips the zero columns."""
+        image_view() strips the zero columns.  ``src_index`` (int32, host or device): the frame each output takes, < 0 =
+        an all-zero raw frame; a host table is range-checked here (no device sync), a device table is trusted — the
+        kernel never reads past ``frames`` (an entry >= n yields a zero raw frame).  ``out``: write into this slice of a
+        larger engine-frame buffer (cross-video batching) instead of allocating."""
         assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
         frames = frames.contiguous()
         n, H, W, _ = frames.shape
         if src_index is not None:
-            src_index = src_index.to(self.device, torch.int32).contiguous()
-            n_out = src_index.numel()
-            if n_out and int(src_index.max()) >= n:
+            if not src_index.is_cuda and src_index.numel() and int(src_index.max()) >= n:
                 raise IndexError("src_index entry beyond the last frame")
+            src_index = src_index.to(self.device, torch.int32, non_blocking=True).contiguous()
+            n_out = src_index.numel()
         else:
             n_out = n
-        out = torch.empty((n_out,) + self.frame_shape, dtype=self.frame_dtype, device=self.device)
+        if out is None:
+            out = torch.empty((n_out,) + self.frame_shape, dtype=self.frame_dtype, device=self.device)
+        else:
+            assert out.is_cuda and out.dtype == self.frame_dtype and out.is_contiguous()
+            assert tuple(out.shape) == (n_out,) + self.frame_shape
         check(self.lib.wd_preprocess_u8(self.h, _ptr(frames), n, H, W, _ptr(src_index), n_out, float(in_scale),
                                         _ptr(out), _stream_ptr(self.device)))
         return out
@@ -215,23 +222,25 @@ class Engine:
         return logits.clone(), probs.clone(), state.clone()   # the pinned staging tensors are reused by later calls
 
     def _host_out(self, n: int):
-        """Pinned result buffers, a ring of four sets per batch size (pinned allocation costs ~0.1 ms per tensor, so
-        they are reused; a returned set is overwritten by the fourth later call with the same n)."""
+        """Pinned result buffers, a ring of five sets per batch size (pinned allocation costs ~0.1 ms per tensor, so
+        they are reused round-robin; a returned set is overwritten by the fifth later call with the same n — the
+        streaming entry point keeps at most three calls in flight)."""
         ring = self._host_ring.setdefault(n, [])
-        if len(ring) < 4:
+        if len(ring) < 5:
             ring.append((torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True),
                          torch.empty((n, self.num_class), dtype=torch.float32, pin_memory=True),
                          torch.empty((n,), dtype=torch.int32, pin_memory=True)))
             return ring[-1]
-        self._host_next[n] = (self._host_next.get(n, 0) + 1) % 4
-        return ring[self._host_next[n]]
+        i = self._host_next.get(n, 0)
+        self._host_next[n] = (i + 1) % 5
+        return ring[i]
 
     def infer_u8_host_async(self, frames: torch.Tensor, in_scale: float = 1.0 / 255.0, threshold: float = 0.5,
                             softmax: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Streaming form: PINNED host uint8 [n_clips*8,H,W,3] is enqueued (H2D -> preprocess -> forward -> D2H) and
-        the call returns pinned (logits, probs, state) that are valid after ``host_sync()``.  Two batches are in
-        flight, so the copy of the next batch overlaps the compute of this one; ``frames`` must stay untouched until
-        the sync."""
+        the call returns pinned (logits, probs, state) that are valid after ``host_sync()``.  Up to three batches are
+        in flight, so the copy of the next batches overlaps the compute of this one; ``frames`` must stay untouched
+        until the sync."""
         assert not frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and frames.is_pinned()
         F, H, W, _ = frames.shape
         assert F % 8 == 0
@@ -267,6 +276,25 @@ def count_reps(states: torch.Tensor, lens: Optional[torch.Tensor] = None, step: 
     check(lib.wd_count_reps(_ptr(states), _ptr(lens), V, W, int(step), _ptr(counts), _ptr(reps), stride,
                             _ptr(reps_len), _stream_ptr(states.device)))
     return counts, reps, reps_len
+
+
+def vote_states(labels: torch.Tensor, lens: Optional[torch.Tensor] = None, window: int = 7, votes: int = 4):
+    """Majority vote of count_by_image_model (utils/inference_count.py:211-231) on the GPU.
+
+    labels: cuda int32 [V, F] per-frame arg-max classes; lens: cuda int32 [V] or None.
+    Returns states int32 [V, F]: (sum of the last ``window`` labels >= votes) as 0 / 1, -1 past lens[v].
+    """
+    if not labels.is_cuda:
+        raise RuntimeError("vote_states needs CUDA tensors; there is no CPU fallback")
+    lib = _lib.load()
+    labels = labels.to(torch.int32).contiguous()
+    V, F = labels.shape
+    if lens is not None:
+        lens = lens.to(labels.device, torch.int32).contiguous()
+    states = torch.empty_like(labels)
+    check(lib.wd_vote_states(_ptr(labels), _ptr(lens), V, F, int(window), int(votes), _ptr(states),
+                             _stream_ptr(labels.device)))
+    return states
 
 
 def scores_to_states(scores: torch.Tensor, threshold: float = 0.5, softmax: bool = True):

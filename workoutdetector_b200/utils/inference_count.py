@@ -24,7 +24,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
-from ..engine import count_reps
+from ..engine import count_reps, scores_to_states, vote_states
 from ..settings import PROJ_ROOT, REPCOUNT_ANNO_PATH
 
 COLORS = {
@@ -225,6 +225,97 @@ def count_by_video_model(model, video_path: str, ground_truth: Optional[list] = 
 
 
 # --------------------------------------------------------------------------------------------------
+# image-model counting (per-frame classifier -> 7-frame majority vote -> counter)
+# --------------------------------------------------------------------------------------------------
+def _image_transform():
+    """The reference's module-level ``data_transform`` (inference_count.py:27-34), built lazily."""
+    import torchvision.transforms as T
+    return T.Compose([T.ToPILImage(), T.Resize(256), T.CenterCrop(224), T.ToTensor(),
+                      T.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+
+
+def inference_image(model, frame: np.ndarray) -> np.ndarray:
+    """Scores of one frame from an image classifier (reference inference_count.py:168-189).
+
+    model: an onnxruntime-style session (``get_inputs()`` / ``run()``), a torch module, or any callable that maps
+    the transformed ``[1,3,224,224]`` tensor to scores ``[1,C]``.  frame: cv2 image (H, W, 3), fed as the reference
+    feeds it (no BGR->RGB conversion there).  Returns float32 [C].
+    """
+    x = _image_transform()(frame).unsqueeze(0)
+    if _is_ort_like(model):
+        input_name = model.get_inputs()[0].name
+        score = model.run(None, {input_name: x.numpy()})[0][0]
+    else:
+        if isinstance(model, torch.nn.Module):
+            p = next(model.parameters(), None)
+            if p is not None:
+                x = x.to(p.device)
+        with torch.no_grad():
+            score = model(x)
+        score = score.detach().cpu().numpy()[0] if isinstance(score, Tensor) else np.asarray(score)[0]
+    return np.asarray(score).astype(np.float32)
+
+
+def vote_and_count(frame_scores: Union[Tensor, np.ndarray], lens: Optional[Tensor] = None, window: int = 7,
+                   votes: int = 4, step: int = 7) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """The tail of count_by_image_model (inference_count.py:211-235), batched over videos on the GPU.
+
+    frame_scores: per-frame scores [V, F, C] (float) or per-frame arg-max labels [V, F] (integer).
+    Returns (states [V,F] i32 — the 0/1 vote, -1 past lens —, counts [V], reps [V,F+1], reps_len [V]).
+    Three kernels: first-max arg-max (scores_to_states_kernel), vote_states_kernel, count_reps_kernel.
+    """
+    if not torch.cuda.is_available():
+        raise RuntimeError("vote_and_count runs on the GPU kernels; no CUDA device is visible")
+    x = torch.from_numpy(frame_scores) if isinstance(frame_scores, np.ndarray) else frame_scores
+    x = x.to("cuda")
+    if x.dim() == 3:
+        V, F, C = x.shape
+        # numpy's argmax = first maximum; no softmax, no threshold (the reference's `threshold` argument is unused)
+        _, labels = scores_to_states(x.reshape(V * F, C).float(), threshold=float("-inf"), softmax=False)
+        labels = labels.view(V, F)
+    else:
+        labels = x.to(torch.int32)
+    states = vote_states(labels, lens, window, votes)
+    counts, reps, reps_len = count_reps(states, lens, step)
+    return states, counts, reps, reps_len
+
+
+def count_by_image_model(model, video_path: str, ground_truth: Optional[List[int]] = None,
+                         video_out_path: Optional[str] = None, pred_out_path: Optional[str] = None,
+                         threshold: float = 0.1) -> Tuple[int, List[int]]:
+    """Count repetitions with a per-frame image classifier (reference inference_count.py:192-243).
+
+    Every frame is scored by ``model`` (see inference_image; a model with a ``score_frames(frames_bgr_u8) -> [F,C]``
+    method is called once for the whole video instead); the arg-max labels go through the 7-frame majority vote
+    (state = sum of the last 7 labels >= 4) and ``pred_to_count(step=7)`` on the GPU.  ``threshold`` is accepted and,
+    as in the reference, not used.
+    """
+    print(f'{video_path}')
+    frames = read_video_frames(video_path, rgb=False)      # the reference feeds cv2's BGR frames as they are
+    if hasattr(model, "score_frames"):
+        sc = model.score_frames(frames)
+        scores = np.asarray(sc.detach().cpu() if isinstance(sc, Tensor) else sc, dtype=np.float32)
+    else:
+        scores = np.stack([inference_image(model, f) for f in frames.numpy()]) if frames.shape[0] else \
+            np.zeros((0, 1), np.float32)
+    if scores.shape[0] == 0:
+        states, count, reps = [], 0, []
+    else:
+        st, counts, reps_t, reps_len = vote_and_count(torch.from_numpy(scores).unsqueeze(0))
+        states = st[0].tolist()
+        count = int(counts[0])
+        reps = reps_t[0, :int(reps_len[0])].tolist()
+    gt_count = len(ground_truth) // 2 if ground_truth else -1
+    correct = (abs(count - gt_count) <= 1)
+    print(f'count={count} gt_count={gt_count} correct={correct}')
+    if pred_out_path:
+        save_scores_to_json(list(scores), pred_out_path, video_path, step=1)
+    if video_out_path:
+        write_to_video(video_path, video_out_path, reps, states, step=7)
+    return count, reps
+
+
+# --------------------------------------------------------------------------------------------------
 # score files
 # --------------------------------------------------------------------------------------------------
 def save_scores_to_json(scores: List[np.ndarray], output_path: str, video_path: str, step: int) -> None:
@@ -323,7 +414,8 @@ def eval_dataset(model, action: List[str], split: str, model_type: str = 'video'
             count, reps = count_by_video_model(model, item.video_path, ground_truth=item.reps,
                                                video_out_path=output_path)
         elif model_type == 'image':
-            raise NotImplementedError("the image-model path (count_by_image_model) is not on the B200 engine")
+            count, reps = count_by_image_model(model, item.video_path, ground_truth=item.reps,
+                                               video_out_path=output_path, pred_out_path=None, threshold=threshold)
         else:
             raise ValueError(f'Invalid model type: {model_type}')
         pred_dict[name] = count
@@ -366,6 +458,9 @@ def main(args) -> None:
     model = create_model(num_class=args.num_class, num_segments=8, base_model='resnet50',
                          checkpoint=args.checkpoint, device='cuda')
     if not args.eval and args.video is not None:
+        if args.model_type == 'image':
+            raise SystemExit("the CLI builds a TSM video model; count_by_image_model takes a per-frame classifier "
+                             "(call it from Python)")
         count_by_video_model(model, args.video, ground_truth=[], video_out_path=args.output,
                              threshold=args.threshold)
     elif args.eval:

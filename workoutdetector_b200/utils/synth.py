@@ -47,3 +47,15 @@ def synth_video_u8(n_frames: int, seed: int, period: float = 48.0, H: int = 224,
         img = a * (1 - w) + b * w + (torch.rand(3, H, W, generator=g) - 0.5) * 0.04
         out.append((img.clamp(0, 1) * 255).round().to(torch.uint8).permute(1, 2, 0))
     return torch.stack(out).contiguous()
+
+
+def synth_frames_u8(n: int, H: int, W: int, seed: int) -> torch.Tensor:
+    """[n, H, W, 3] uint8 frames of any geometry: a sinusoidal pattern (integer-exact, platform independent) plus seeded
+    integer noise — the input of the preprocessing goldens for non-224 geometries."""
+    g = torch.Generator().manual_seed(seed)
+    yy = torch.arange(H, dtype=torch.int64).view(H, 1, 1)
+    xx = torch.arange(W, dtype=torch.int64).view(1, W, 1)
+    ch = torch.arange(3, dtype=torch.int64).view(1, 1, 3)
+    base = ((yy * 7 + xx * 5 + ch * 40) % 200) + ((yy // 9 + xx // 7) % 2) * 30       # integer arithmetic only
+    noise = torch.randint(-12, 13, (n, H, W, 3), generator=g)
+    return (base.unsqueeze(0) + noise).clamp(0, 255).to(torch.uint8)
