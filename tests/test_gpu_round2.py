@@ -145,3 +145,186 @@ def test_preprocess_vs_reference_transform_golden_downscale(weights, golden_dir,
         gq = e.image_view(e.preprocess_u8(u8, in_scale=1.0).float().cpu()).permute(0, 3, 1, 2)[:, :, rows][:, :, :, rows].numpy()
         assert np.abs(gq - quirk).max() <= max(tol, 3e-6) * np.abs(quirk).max(), mode
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[1] at its own size: 64 clips, bf16 engine vs the fp32 oracle, directly
+# ---------------------------------------------------------------------------------------------------
+def test_batch64_bf16_softmax_vs_oracle_direct(weights):
+    """One 64-clip forward (the bench batch) against the oracle on the same 64 clips: softmax within 2e-2, top-1 state
+    identical wherever the oracle's margin exceeds the tolerance."""
+    from workoutdetector_b200.engine import Engine
+    sd = weights["rand"]
+    u8 = synth_clips_u8(64, 31)
+    with torch.no_grad():
+        ref = O.tsm_forward(sd, O.preprocess_u8(u8))
+    pref, sref = O.scores_to_states(ref)
+    e = Engine(12, max_clips=64)
+    e.load_state_dict(sd)
+    logits, probs, st = e.forward(e.preprocess_u8(u8.cuda()))
+    err = float((probs.cpu() - pref).abs().max())
+    assert err < TOL_BF16, err
+    top2 = pref.topk(2, dim=1).values
+    decided = ((top2[:, 0] - top2[:, 1]) > 2 * TOL_BF16) & ((top2[:, 0] - 0.5).abs() > TOL_BF16)
+    assert torch.equal(st.cpu()[decided], sref[decided]) and int(decided.sum()) >= 32
+    assert float((pref.max(0).values - pref.min(0).values).max()) > 0.02     # not vacuous: the clips do not score alike
+    e.close()
+
+
+def test_tdn_16_clips_bf16_vs_oracle():
+    """TDN-R50 at 16 clips (configs[4] is batch 128; the oracle takes seconds per clip): softmax within 2e-2 of the fp32
+    oracle, and batch composition does not change a clip's result (16 at once == 4 x 4)."""
+    from oracle import tdn_oracle as T
+    from workoutdetector_b200.engine import Engine
+    sd = T.random_state_dict(12, 5)
+    g = torch.Generator().manual_seed(17)
+    base = T.golden_input()                                   # [2,8,5,3,224,224]: noise + temporally smooth frames
+    x = torch.cat([base * (0.6 + 0.1 * i) + 0.05 * torch.randn(base.shape, generator=g) for i in range(8)])
+    with torch.no_grad():
+        ref = T.tdn_forward(sd, x)
+    pref = torch.softmax(ref, 1)
+    e = Engine(12, max_clips=16, arch="tdn")
+    e.load_state_dict(sd)
+    logits, probs, st = e.forward(e.pack_tdn(x.cuda()))
+    assert float((probs.cpu() - pref).abs().max()) < TOL_BF16
+    parts = [e.forward(e.pack_tdn(x[i:i + 4].cuda()))[0] for i in range(0, 16, 4)]
+    assert torch.equal(torch.cat(parts), logits)
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# dataset-scale driver (configs[2] / configs[3]) on the GPU
+# ---------------------------------------------------------------------------------------------------
+def test_dataset_runner_cross_video_batching(weights, count_oracle_c):
+    """Windows batched ACROSS videos (every forward full) give bit-identical states to scoring video by video, counts
+    equal the C oracle on those states byte for byte, and the summary's MAE / OBO follow utils/eval.py."""
+    from workoutdetector_b200 import dataset_runner as DR
+    from workoutdetector_b200.models import create_model
+    from workoutdetector_b200.utils.inference_count import score_windows, window_index_table
+    m = create_model(12, device="cuda")
+    m.load_state_dict(weights["rand"])
+    lengths = [97, 8, 300, 64, 1, 133, 250, 77, 16, 201]
+    vids = [synth_video_u8(n, 40 + i, period=24.0 + 4 * i).cuda() for i, n in enumerate(lengths)]
+    names = [f"v{i}" for i in range(len(vids))]
+    gt = [n // 40 for n in lengths]
+    summary, stats = DR.run_dataset(m, names, lengths, lambda i: vids[i], gt_counts=gt, batch=16, in_scale=1.0,
+                                    keep_scores=True)
+    W = [(n + 7) // 8 for n in lengths]
+    assert stats["windows"] == sum(W) and stats["forwards"] == (sum(W) + 15) // 16      # every forward but the last is full
+    eng = m.engine(16)
+    st_all = np.full((len(vids), max(W)), -1, np.int32)
+    for i, v in enumerate(vids):
+        lg, pb, st = score_windows(m, v, window_index_table(lengths[i]), in_scale=1.0, batch=16)
+        r = summary["results"][names[i]]
+        assert r["states"] == st.tolist(), names[i]                       # same kernels, same per-clip arithmetic
+        assert np.array_equal(r["scores"], lg.cpu().numpy())
+        st_all[i, :W[i]] = r["states"]
+    lens = np.array(W, np.int32)
+    counts = np.zeros(len(vids), np.int32)
+    reps = np.zeros((len(vids), max(W) + 1), np.int32)
+    rl = np.zeros(len(vids), np.int32)
+    count_oracle_c.oracle_count_reps(st_all.ctypes.data, lens.ctypes.data, len(vids), max(W), 8, counts.ctypes.data,
+                                     reps.ctypes.data, max(W) + 1, rl.ctypes.data)
+    for i, n in enumerate(names):
+        assert summary["counts"][n] == int(counts[i]) and summary["results"][n]["reps"] == reps[i, :rl[i]].tolist()
+    mae, obo = CO.obo_mae([int(c) for c in counts], gt)
+    assert abs(summary["mae"] - mae) < 1e-12 and abs(summary["obo"] - obo) < 1e-12
+    with pytest.raises(IndexError):
+        DR.WindowBatcher(m, batch=16).add_video(vids[1], torch.full((1, 8), 9, dtype=torch.int32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own example video (SURVEY §8 f2): decode -> count -> overlay round trip
+# ---------------------------------------------------------------------------------------------------
+def test_real_example_video_smoke(weights, tmp_path):
+    """tests/data/stu1_40.mp4 is the reference's example_videos/stu1_40.mp4 (ground truth 8 repetitions,
+    datasets/RepCount/annotation.csv:799).  With random-init weights the count itself is meaningless; what is checked:
+    decode, 8-frame queues, engine states == oracle states where the oracle is decided, counter == oracle counter on
+    the engine's states, and write_to_video writes every scored frame back."""
+    from workoutdetector_b200.models import create_model
+    from workoutdetector_b200.utils.inference_count import (count_by_video_model, queue_index_table, read_video_frames,
+                                                            score_windows)
+    path = os.path.join(ROOT, "tests", "data", "stu1_40.mp4")
+    frames = read_video_frames(path)
+    F_, H, W_ = frames.shape[:3]
+    assert F_ > 200 and (H, W_) != (224, 224)                  # a real container with a non-square geometry
+    sd = weights["rand"]
+    m = create_model(12, device="cuda")
+    m.load_state_dict(sd)
+    out = str(tmp_path / "out.mp4")
+    gt = [0, 1] * 8
+    count, reps = count_by_video_model(m, path, ground_truth=gt, video_out_path=out)
+    table = queue_index_table(F_)
+    _, probs, st = score_windows(m, frames, table)
+    assert (count, reps) == CO.pred_to_count(st.tolist(), 8) and len(st) == F_ // 8
+    idx = table[:24].reshape(-1).long()                         # oracle on the first 24 queues (CPU seconds)
+    with torch.no_grad():
+        ref = O.tsm_forward(sd, O.preprocess_u8(frames[idx]))
+    pref, sref = O.scores_to_states(ref)
+    assert float((probs[:24].cpu() - pref).abs().max()) < TOL_BF16
+    top2 = pref.topk(2, dim=1).values
+    decided = ((top2[:, 0] - top2[:, 1]) > 2 * TOL_BF16) & ((top2[:, 0] - 0.5).abs() > TOL_BF16)
+    assert torch.equal(st[:24].cpu()[decided], sref[decided])
+    written = read_video_frames(out)
+    assert written.shape[0] == len(st) * 8 and tuple(written.shape[1:3]) == (H, W_)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ADVICE round 1: stale packed weights, option changes, device side effects
+# ---------------------------------------------------------------------------------------------------
+def test_engine_follows_in_place_weight_edits(weights):
+    from workoutdetector_b200.models import create_model
+    m = create_model(12, device="cuda")
+    m.load_state_dict(weights["rand"])
+    x = O.preprocess_u8(synth_clips_u8(2, 3)).cuda()
+    y0 = m(x).clone()
+    m.fc.weight.data.mul_(2.0)                                  # through .data: no autograd version bump
+    y1 = m(x).clone()
+    assert not torch.allclose(y0, y1) and torch.allclose(y1 - m.fc.bias, 2 * (y0 - m.fc.bias), rtol=2e-2, atol=1e-3)
+    with torch.no_grad():
+        m.fc.bias.add_(1.0)                                     # plain in-place op
+    y2 = m(x).clone()
+    assert torch.allclose(y2, y1 + 1.0, atol=1e-4)
+    m.base_model.load_state_dict({k[len("base_model."):]: v for k, v in weights["init"].items()
+                                  if k.startswith("base_model.")})   # sub-module load: TSM.load_state_dict never runs
+    y3 = m(x).clone()
+    assert not torch.allclose(y3, y2)
+    m.fc = torch.nn.Linear(2048, 12).cuda()                     # replaced head
+    y4 = m(x)
+    assert not torch.allclose(y4, y3)
+    m.refresh_engine()
+    assert torch.equal(m(x), y4)
+
+
+def test_plan_option_change_invalidates_weights(weights):
+    from workoutdetector_b200._lib import WdError
+    from workoutdetector_b200.engine import Engine
+    e = Engine(12, max_clips=2)
+    e.load_state_dict(weights["rand"])
+    fr = e.preprocess_u8(synth_clips_u8(2, 3).cuda())
+    y = e.forward(fr)[0].clone()
+    e.set_option("pdl", 0)                                       # launch-time option: weights stay valid
+    assert torch.equal(e.forward(fr)[0], y)
+    e.set_option("tile_n_max", 128)                              # plan-affecting: forward must fail loudly until reload
+    with pytest.raises(WdError):
+        e.forward(fr)
+    e.load_state_dict(weights["rand"])
+    assert float((e.forward(fr)[0] - y).abs().max()) < 0.05 * float(y.abs().max())
+    e.close()
+
+
+def test_calls_do_not_change_the_current_device(weights):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from workoutdetector_b200.engine import Engine, count_reps
+    torch.cuda.set_device(0)
+    e = Engine(12, max_clips=1, device=1)
+    e.load_state_dict(weights["rand"])
+    assert torch.cuda.current_device() == 0
+    with torch.cuda.device(1):
+        fr = e.preprocess_u8(synth_clips_u8(1, 3).to("cuda:1"))
+        st = e.forward(fr)[2]
+    assert torch.cuda.current_device() == 0
+    c, _, _ = count_reps(st.view(1, 1))                          # tensors on cuda:1 while cuda:0 is current
+    assert c.device.index == 1 and torch.cuda.current_device() == 0
+    e.close()

@@ -20,6 +20,7 @@ from torch import nn
 from torch.nn.init import constant_, normal_
 
 from ..engine import Engine
+from . import _sync
 
 
 class mSEModule(nn.Module):
@@ -173,6 +174,7 @@ class TSN(nn.Module):
 
         self._engine: Optional[Engine] = None
         self._engine_dirty = True
+        self._engine_state = None
         self._engine_mode = os.environ.get("WD_B200_MODE", "bf16")
         self._max_clips = 4
 
@@ -199,10 +201,18 @@ class TSN(nn.Module):
             self._max_clips = max(self._max_clips, n_clips)
             self._engine = Engine(self.num_class, max_clips=self._max_clips, mode=self._engine_mode, device=idx,
                                   arch="tdn")
-        if self._engine_dirty:
+        # weights changed behind the engine's back (in-place edits, optimizer steps, sub-module load_state_dict, a
+        # replaced fc)?  models/_sync.py: version / pointer fingerprint + content checksum
+        state = _sync.state_of(self)
+        if self._engine_dirty or state != self._engine_state:
             self._engine.load_state_dict(self.state_dict())
             self._engine_dirty = False
+            self._engine_state = state
         return self._engine
+
+    def refresh_engine(self) -> None:
+        """Re-upload the module's current parameters on the next forward, unconditionally."""
+        self._engine_dirty = True
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
