@@ -715,10 +715,11 @@ def test_fused_conv3_conv1_equals_unfused(weights):
     out = {}
     for flag in ("2", "1", "0"):
         os.environ["WD_FUSE2"] = flag
+        os.environ["WD_FUSE3"] = "0"       # the layer-2 fusion has its own test (tests/test_gpu_round2.py)
         try:
             e = Engine(12, max_clips=5)
         finally:
-            del os.environ["WD_FUSE2"]
+            del os.environ["WD_FUSE2"], os.environ["WD_FUSE3"]
         e.load_state_dict(weights["rand"])
         names = [o["name"] for o in e.ops()]
         assert ("layer1.1.conv1" in names) == (flag == "0") and ("layer2.0.conv1" in names) == (flag != "2")

@@ -328,3 +328,44 @@ def test_calls_do_not_change_the_current_device(weights):
     c, _, _ = count_reps(st.view(1, 1))                          # tensors on cuda:1 while cuda:0 is current
     assert c.device.index == 1 and torch.cuda.current_device() == 0
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# layer-2 conv3 + next conv1 in one kernel (wd_conv_fuse3.cuh)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_clips", [5, 40])
+def test_fused_layer2_conv3_conv1_equals_unfused(weights, n_clips):
+    """conv_fuse3_kernel (chunked 512-wide output tile, A operand of the second GEMM in tensor memory, streamed weights,
+    TemporalShift fold 64 as a warp shuffle) against the same network with the two convolutions as separate kernels
+    (WD_FUSE3=0): same bf16 products and the same fp32 accumulation order -> bit-identical activations and logits.
+    40 clips = 245 tiles: more than one tile per CTA, so the cross-tile pipeline (accumulator hand-over, ring wrap) runs."""
+    from workoutdetector_b200.engine import Engine
+    x = torch.randn(n_clips * 8, 3, 224, 224, generator=torch.Generator().manual_seed(23)).cuda()
+    out, taps = {}, {}
+    for flag, safe in (("1", "1"), ("1", "0"), ("0", "1")):
+        os.environ["WD_FUSE3"] = flag
+        os.environ["WD_FUSE3_SAFE"] = safe
+        try:
+            e = Engine(12, max_clips=n_clips)
+        finally:
+            del os.environ["WD_FUSE3"], os.environ["WD_FUSE3_SAFE"]
+        e.load_state_dict(weights["rand"])
+        names = [o["name"] for o in e.ops()]
+        fused = flag == "1"
+        assert ("layer2.2.conv1" in names) == (not fused) and ("layer3.0.conv1" in names) == (not fused)
+        assert "layer2.1.conv1" in names and len(names) == (44 if fused else 47)
+        frames = e.pack_nchw(x)
+        key = flag + safe
+        taps[key] = {}
+        for nm in ("layer2.1.conv3", "layer2.3.conv3", "layer2.2.conv2", "layer3.0.conv2", "layer3.0.conv3"):
+            t = e.set_tap(names.index(nm), n_clips)
+            e.forward(frames)
+            torch.cuda.synchronize()
+            taps[key][nm] = t.clone()
+        e.set_tap(-1)
+        out[key] = e.forward(frames)[0].clone()
+        e.close()
+    for key in ("11", "10"):
+        for nm, t in taps[key].items():
+            assert torch.equal(t, taps["01"][nm]), (key, nm, float((t - taps["01"][nm]).abs().max()))
+        assert torch.equal(out[key], out["01"]), key

@@ -23,6 +23,7 @@
 #include "wd_stem_pool.cuh"
 #include "wd_tdn_kernels.cuh"
 #include "wd_conv_fuse2.cuh"
+#include "wd_conv_fuse3.cuh"
 #include "wd_conv_strip2.cuh"
 
 namespace {
@@ -204,6 +205,9 @@ struct wd_engine {
     int fuse_ds_requested = 2;  // WD_FUSE_DS at create time
     int fuse2 = 1;              // layer-1 conv3 + next conv1 in one kernel (needs fuse_ds >= 1 and 256-wide tiles)
     int fuse2_requested = 1;    // WD_FUSE2 at create time
+    int fuse3 = 1;              // layer-2 conv3 + next conv1 in one kernel (wd_conv_fuse3.cuh); WD_FUSE3 at create time
+    int fuse3_requested = 1;
+    int fuse3_safe = 1;         // WD_FUSE3_SAFE at create time: explicit barrier between M2(g) and M1(g+2) (wd_conv_fuse3.cuh)
     int use_2cta = 4;          // per-engine copies of the launch-helper switches (set_option "use_2cta" / "pdl" /
     int pdl = 1;               // "prefetch_kblocks"); run_forward installs them before launching
     int prefetch_kblocks = -1;
@@ -389,6 +393,23 @@ int build_plan(wd_engine* e) {
                 const std::string nb = last ? "layer2.0" : "layer1." + std::to_string(b + 1);
                 pre_c1 = add_conv(nb + ".conv1", "base_model." + nb + ".conv1.net.weight", "base_model." + nb + ".conv1.weight",
                                   "base_model." + nb + ".bn1", outp, last ? planes[1] : width, 1, 1, Ho,
+                                  outp / e->desc.shift_div, 1);
+                e->convs[pre_c1].fused_next = true;
+                pre_buf = o1;
+                Op& o3 = e->ops.back();
+                o3.conv2 = pre_c1;
+                o3.out2_buf = o1;
+                o3.macs_per_clip += 8.0 * Ho * Ho * (double)e->convs[pre_c1].Cout * outp;
+            }
+            // Layer 2, blocks with an identity residual: the same fusion with streamed weights and a chunked output tile
+            // (wd_conv_fuse3.cuh).  The next conv1 is 512 -> 128 inside layer 2 and layer3.0.conv1 (512 -> 256, still
+            // 28 x 28) after the last block.
+            if (e->fuse3 && L == 1 && b > 0 && e->desc.mode == WD_MODE_BF16 && e->desc.is_shift && outp == 512 &&
+                outp / e->desc.shift_div == 64 && e->tile_n_max == 256 && e->use_tma_a && e->persistent >= 3) {
+                const bool last = b + 1 == blocks[L];
+                const std::string nb = last ? "layer3.0" : "layer2." + std::to_string(b + 1);
+                pre_c1 = add_conv(nb + ".conv1", "base_model." + nb + ".conv1.net.weight", "base_model." + nb + ".conv1.weight",
+                                  "base_model." + nb + ".bn1", outp, last ? planes[2] : width, 1, 1, Ho,
                                   outp / e->desc.shift_div, 1);
                 e->convs[pre_c1].fused_next = true;
                 pre_buf = o1;
@@ -1400,6 +1421,48 @@ int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool h
     return has_res ? launch_fuse2_t<true, 128>(e, c3, c1n, n_clips, st) : launch_fuse2_t<false, 128>(e, c3, c1n, n_clips, st);
 }
 
+// Layer 2: conv3 (+ identity residual) of a block + conv1 of the next block in one kernel (wd_conv_fuse3.cuh).
+template <int N2>
+int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int n_clips, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_fuse3_kernel<N2>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Fuse3Args p{};
+    p.bias1 = c3.bias;
+    p.bias2 = c1n.bias;
+    p.M = n_clips * c3.Hout * c3.Wout * 8;
+    if (p.M % wd::kTileM != 0) return fail(WD_ERR_INVALID, "%s: %d rows are not a multiple of 128", c3.name.c_str(), p.M);
+    p.num_tiles = p.M / wd::kTileM;
+    p.n_chunks = c3.Cout / wd::kF3Chunk;
+    p.shift = c1n.fold == 64 ? 1 : 0;
+    p.safe_order = e->fuse3_safe;
+    p.w_stages = 3;
+    p.res_depth = 2;
+    // shared memory: 2 A slots (32 KiB each) | W ring | 8 output slabs | residual ring | barriers
+    p.off_w = 2 * 32768;
+    p.off_out = p.off_w + p.w_stages * wd::kF3WStage;
+    p.off_res = p.off_out + 8 * wd::kEpiSlab;
+    p.off_bar = p.off_res + 4 * p.res_depth * wd::kEpiSlab;
+    const size_t smem = (size_t)p.off_bar + 1024 + 1024;
+    if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1 (layer 2): %zu bytes of shared memory", smem);
+    const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
+    WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kF3Threads, smem, st, c3.wmap_half, c1n.wmap, c3.amap, c3.omap, c3.rmap,
+                       c1n.omap, p));
+    return WD_OK;
+}
+
+int launch_fuse3(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool has_res, int n_clips, cudaStream_t st) {
+    if (!has_res || c3.tile_n != 256 || c3.Cout % 256 != 0 || c3.Cin != 128 || c3.kblocks != 2 || c3.kb_split != 0 ||
+        c3.a_mode != wd::A_TMA || c1n.Cin != c3.Cout || (c1n.Cout != 128 && c1n.Cout != 256) || c1n.tile_n != c1n.Cout ||
+        (c1n.fold != 64 && c1n.fold != 0) || c3.Cout != 512)
+        return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused layer-2 conv3 + conv1 kernel", c3.name.c_str(),
+                    c1n.name.c_str());
+    return c1n.Cout == 128 ? launch_fuse3_t<128>(e, c3, c1n, n_clips, st) : launch_fuse3_t<256>(e, c3, c1n, n_clips, st);
+}
+
 // Motion excitation + temporal Conv1d of one BottleneckShift: four launches (wd_tdn_kernels.cuh).
 template <typename T, int R>
 int launch_mse(const MseLayer& ml, const void* in, void* out, float* scratch, int n_clips, cudaStream_t st) {
@@ -1482,6 +1545,8 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 dim3 grid((a.M + 3) / 4, (c.Cout + 63) / 64);
                 wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
                 WD_CUDA(cudaGetLastError());
+            } else if (o.conv2 >= 0 && c.Cout == 512) {
+                WD_TRY(launch_fuse3(e, c, e->convs[o.conv2], res != nullptr, n_clips, st));
             } else if (o.conv2 >= 0) {
                 WD_TRY(launch_fuse2(e, c, e->convs[o.conv2], res != nullptr, n_clips, st));
             } else if (o.in_buf == kInDiff && c.a_mode == wd::A_TAP) {
@@ -1679,6 +1744,9 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->fuse_ds = e->fuse_ds_requested;
     e->fuse2_requested = getenv("WD_FUSE2") ? atoi(getenv("WD_FUSE2")) : 2;  // 1: inside layer 1, 2: + layer2.0.conv1
     e->fuse2 = e->fuse2_requested;
+    e->fuse3_requested = getenv("WD_FUSE3") ? atoi(getenv("WD_FUSE3")) : 1;
+    e->fuse3 = d->arch == WD_ARCH_TSM_R50 ? e->fuse3_requested : 0;
+    e->fuse3_safe = getenv("WD_FUSE3_SAFE") ? atoi(getenv("WD_FUSE3_SAFE")) : 1;
     int r = d->arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e);
     if (r != WD_OK) {
         delete e;
@@ -1785,7 +1853,9 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     {
         const int want_fuse = (e->use_tma_a && e->persistent >= 3) ? e->fuse_ds_requested : 0;
         const int want_f2 = (want_fuse >= 1 && e->tile_n_max == 256) ? e->fuse2_requested : 0;
-        if (want_fuse != e->fuse_ds || want_f2 != e->fuse2) {
+        const int want_f3 = (e->desc.arch == WD_ARCH_TSM_R50 && e->use_tma_a && e->persistent >= 3 && e->tile_n_max == 256)
+                                ? e->fuse3_requested : 0;
+        if (want_fuse != e->fuse_ds || want_f2 != e->fuse2 || want_f3 != e->fuse3) {
             for (auto& c : e->convs) {
                 if (c.w_packed) cudaFree(c.w_packed);
                 if (c.bias) cudaFree(c.bias);
@@ -1798,6 +1868,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             e->mses.clear();
             e->fuse_ds = want_fuse;
             e->fuse2 = want_f2;
+            e->fuse3 = want_f3;
             e->tap_idx = -1;
             WD_TRY(e->desc.arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e));
         }
