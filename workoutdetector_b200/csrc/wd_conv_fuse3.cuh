@@ -13,23 +13,23 @@
 // profiles/r01_ncu_step_batch64.txt: 158 + 90 us); fused, the traffic is y2 + residual + y + z.
 //
 // Tensor memory (512 columns): acc1[0] = [0,128), acc1[1] = [128,256) (chunk g uses buffer g & 1; the packed bf16 chunk
-// lands in the first 64 columns of its own buffer), acc2 = [256, 256 + N2).
+// lands in columns [0,32) and [64,96) of its own buffer: each epilogue warp writes into the columns it drained itself),
+// acc2 = [256, 256 + N2).
 // MMA issue order over the global chunk sequence g = 0,1,2,...:  M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | M2(2) M1(4) ...
 // M1(g+2) overwrites the buffer chunk g lived in; it is issued after M2(g), which is issued after the epilogue has
 // signalled y_full(g) — tcgen05.mma instructions of one thread execute in issue order, so no further barrier is needed.
 // TemporalShift of the second convolution (fold 64 of 512 channels: channels 0..63 from segment t+1, 64..127 from t-1,
 // zeros at the ends) touches chunk 0 only: its first 64-column unit is shuffled down one lane, its second one up (the 8
 // segments of a pixel are 8 adjacent rows of the tile = 8 adjacent lanes).
-// Warp roles (224 threads): 0-3 epilogue, 4 W producer, 5 MMA issuer, 6 A producer.
+// Warp roles (352 threads): 0-7 epilogue (two per scheduler), 8 W producer, 9 MMA issuer, 10 A producer.
 #pragma once
 #include "wd_conv_fuse2.cuh"
 
 namespace wd {
 
 constexpr int kF3Chunk = 128;          // output channels per chunk of the first GEMM
-constexpr int kF3Threads = 224;
+constexpr int kF3Threads = 352;         // warps 0-7 epilogue, 8 W producer, 9 MMA issuer, 10 A producer
 constexpr int kF3WStage = 32768;       // one ring stage: two {64 x 128} boxes or one {64 x 256} box
-constexpr int kF3ResDepthMax = 3;
 
 struct Fuse3Args {
     const float* bias1;   // [N1]  conv3 folded BN shift
@@ -38,11 +38,10 @@ struct Fuse3Args {
     int num_tiles;        // M / 128
     int n_chunks;         // N1 / 128 (4)
     int w_stages;         // ring depth (3)
-    int res_depth;        // residual slabs in flight per epilogue warp (2)
     int shift;            // 1: the second convolution sees TemporalShift(y), fold 64
     int safe_order;       // 1: M1(g+2) is issued only after M2(g) has COMPLETED (y_free barrier) instead of relying on the
                           // in-order execution of tcgen05.mma for the write-after-read on chunk g's TMEM columns
-    int off_w, off_out, off_res, off_bar;   // byte offsets; the A slots (2 x 32 KiB) start at 0
+    int off_w, off_out, off_bar;   // byte offsets; the A slots (2 x 32 KiB) start at 0
 };
 
 template <int N2>
@@ -60,8 +59,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                      // 2 slots x (2 k-blocks x 16 KiB)
     uint8_t* sW = smem + a.off_w;
-    uint8_t* sOut = smem + a.off_out;
-    uint8_t* sRes = smem + a.off_res;
+    uint8_t* sOut = smem + a.off_out;        // 8 warps x 3 slabs x 4 KiB: residual in, result out (in place)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
     uint64_t* a_full = bars;                 // [2]
     uint64_t* a_empty = bars + 2;            // [2]
@@ -72,8 +70,8 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
     uint64_t* acc2_full = bars + 24;         // [1]
     uint64_t* acc2_empty = bars + 25;        // [1]
     uint64_t* y_free = bars + 26;            // [2]  M2(g) has finished reading chunk g from its accumulator buffer
-    uint64_t* res_bar = bars + 32;           // [4 warps][kF3ResDepthMax]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 48);
+    uint64_t* res_bar = bars + 32;           // [8 warps][3 slabs]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 60);
 
     pdl_launch_dependents();
     const int tid = threadIdx.x;
@@ -82,7 +80,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
     const int num_tiles = a.num_tiles;
     const int n_chunks = a.n_chunks;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             tma_prefetch_desc(&w1map);
             tma_prefetch_desc(&w2map);
@@ -94,7 +92,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                 mbar_init(&a_full[s], 1);
                 mbar_init(&a_empty[s], 1);
                 mbar_init(&acc1_full[s], 1);
-                mbar_init(&y_full[s], 4);
+                mbar_init(&y_full[s], 8);
                 mbar_init(&y_free[s], 1);
             }
             for (int s = 0; s < 8; ++s) {
@@ -102,13 +100,13 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                 mbar_init(&w_empty[s], 1);
             }
             mbar_init(acc2_full, 1);
-            mbar_init(acc2_empty, 4);
-            for (int s = 0; s < 4 * kF3ResDepthMax; ++s) mbar_init(&res_bar[s], 1);
+            mbar_init(acc2_empty, 8);
+            for (int s = 0; s < 8 * 3; ++s) mbar_init(&res_bar[s], 1);
             fence_barrier_init();
         }
         __syncwarp();
     }
-    if (warp == 5) {
+    if (warp == 9) {
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
@@ -116,144 +114,142 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
-    if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
+    if (warp != 8 && warp != 9) pdl_grid_dependency_wait();
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ==========================================================================================
-        // Epilogue warps.  Per tile: n_chunks chunks of two 64-column units (bias, residual, ReLU -> slab -> TMA store,
-        // and the packed bf16 back into TMEM), then the N2 / 64 units of the second accumulator.
+        // Epilogue: EIGHT warps, two per scheduler (a single warp per scheduler runs a 64-column unit as one dependent
+        // chain of ~1.6k cycles: residual wait -> LDS -> tcgen05.ld -> math -> STS -> TMA store -> tcgen05.st).  Warps
+        // q and q + 4 share TMEM lane quarter q; `half` = warp >> 2 picks the 64-column unit of every chunk the warp
+        // owns, so a warp runs ONE unit per chunk (+ N2 / 128 units of the second accumulator per tile).
+        // The residual is added IN PLACE in the slab the TMA load delivered it to, which is then the source of the TMA
+        // store: three 4 KiB slabs per warp, unit n uses slab n % 3, the residual of unit n + 2 is requested at the end
+        // of unit n (after the store of unit n - 1, the slab's previous user, has finished reading it).
         // ==========================================================================================
-        uint8_t* my_out = sOut + warp * 2 * kEpiSlab;
-        uint8_t* my_res = sRes + warp * a.res_depth * kEpiSlab;
-        uint64_t* my_res_bar = res_bar + warp * kF3ResDepthMax;
+        const int quarter = warp & 3, half = warp >> 2;
+        uint8_t* my_slab = sOut + warp * 3 * kEpiSlab;
+        uint64_t* my_res_bar = res_bar + warp * 3;
         const uint32_t row_off = lane * 128;
         const uint32_t sw = lane & 7;
         const int t_seg = lane & 7;   // segment of this lane's row (tiles start at multiples of 128 rows)
-        const int units_per_tile = 2 * n_chunks;
+        constexpr int kE2Units = N2 / 128;                    // units of the second accumulator per warp and tile
+        const int upt = n_chunks + kE2Units;                  // this warp's units per tile
         const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const uint32_t total_res = (uint32_t)my_tiles * (uint32_t)units_per_tile;
-        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-        uint32_t res_issue = 0, res_idx = 0, slab_idx = 0, g = 0;
+        const uint32_t total_units = (uint32_t)my_tiles * (uint32_t)upt;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        // request the residual slab of unit n (if it is a first-epilogue unit) into slab n % 3
+        auto request = [&](uint32_t n) {
+            if (n >= total_units) return;
+            const uint32_t r = n % (uint32_t)upt;
+            if (r >= (uint32_t)n_chunks) return;               // second-epilogue unit: no residual
+            const int t2 = (int)blockIdx.x + (int)(n / (uint32_t)upt) * (int)gridDim.x;
+            const uint32_t slot = n % 3u;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&my_res_bar[slot], kEpiSlab);
+                tma_load_2d(&rmap, &my_res_bar[slot], my_slab + slot * kEpiSlab, (int)r * kF3Chunk + half * 64,
+                            t2 * kTileM + quarter * 32);
+            }
+            __syncwarp();
+        };
+        request(0);
+        request(1);
+        uint32_t n = 0, g = 0;
+        uint32_t res_uses[3] = {0, 0, 0};                      // completed residual loads per slot (barrier parity)
         int tile_iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-            const int mrow = tile * kTileM + warp * 32;
+            const int mrow = tile * kTileM + quarter * 32;
 #pragma unroll 1
-            for (int j = 0; j < n_chunks; ++j, ++g) {
+            for (int j = 0; j < n_chunks; ++j, ++g, ++n) {
                 const uint32_t buf = g & 1u;
-                const uint32_t tbuf = lane_base + buf * 128;
-#pragma unroll 1
-                for (int u = 0; u < 2; ++u, ++slab_idx) {
-                    const int col0 = j * kF3Chunk + u * 64;
-                    __syncwarp();
-                    while (res_issue < total_res && res_issue < res_idx + a.res_depth) {
-                        const uint32_t slot = res_issue % a.res_depth;
-                        const uint32_t ut = res_issue % (uint32_t)units_per_tile;
-                        const int t2 = (int)blockIdx.x + (int)(res_issue / (uint32_t)units_per_tile) * (int)gridDim.x;
-                        if (elect_one()) {
-                            mbar_arrive_expect_tx(&my_res_bar[slot], kEpiSlab);
-                            tma_load_2d(&rmap, &my_res_bar[slot], my_res + slot * kEpiSlab, (int)ut * 64,
-                                        t2 * kTileM + warp * 32);
-                        }
-                        __syncwarp();
-                        ++res_issue;
-                    }
-                    if (u == 0) {
-                        mbar_wait(&acc1_full[buf], (g >> 1) & 1u);
-                        tc_fence_after_sync();
-                    }
-                    uint4 rr[8];
-                    {
-                        const uint32_t rslot = res_idx % a.res_depth;
-                        mbar_wait(&my_res_bar[rslot], (res_idx / a.res_depth) & 1u);
-                        const uint8_t* rbuf = my_res + rslot * kEpiSlab + row_off;
+                const uint32_t tbuf = lane_base + buf * 128 + half * 64;   // this warp's 64 accumulator columns
+                const int col0 = j * kF3Chunk + half * 64;
+                const uint32_t slot = n % 3u;
+                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
+                mbar_wait(&acc1_full[buf], (g >> 1) & 1u);
+                tc_fence_after_sync();
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tbuf, v0);
+                tmem_ld32(tbuf + 32, v1);
+                // the slot index is data dependent; keep the three counters in registers
+                const uint32_t uses = slot == 0 ? res_uses[0] : (slot == 1 ? res_uses[1] : res_uses[2]);
+                mbar_wait(&my_res_bar[slot], uses & 1u);
+                if (slot == 0) ++res_uses[0]; else if (slot == 1) ++res_uses[1]; else ++res_uses[2];
+                tmem_ld_wait();
+                uint32_t pk[32];   // 64 bf16 of this row, packed: what goes back to TMEM
+                const float4* bsrc = reinterpret_cast<const float4*>(a.bias1 + col0);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) rr[q] = *reinterpret_cast<const uint4*>(rbuf + ((q ^ sw) << 4));
-                        ++res_idx;
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
+                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
+                    uint4* cell = reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4));
+                    const uint4 rq = *cell;
+                    float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                  __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                  __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                  __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        f[2 * e] += __uint_as_float(rw[e] << 16);
+                        f[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
                     }
-                    float4 bb[16];
-                    const float4* bsrc = reinterpret_cast<const float4*>(a.bias1 + col0);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) bb[q] = __ldg(bsrc + q);
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(tbuf + u * 64, v0);
-                    tmem_ld32(tbuf + u * 64 + 32, v1);
-                    tmem_ld_wait();
-                    if (elect_one()) tma_store_wait_read1();
-                    __syncwarp();
-                    uint8_t* obuf = my_out + (slab_idx & 1) * kEpiSlab + row_off;
-                    uint32_t pk[32];   // 64 bf16 of this row, packed: what goes back to TMEM
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
-                        const float4 b0 = bb[2 * q], b1 = bb[2 * q + 1];
-                        float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
-                                      __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
-                                      __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
-                                      __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
-                        const uint32_t rw[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            f[2 * e] += __uint_as_float(rw[e] << 16);
-                            f[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
-                        }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) pk[q * 4 + e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);   // conv3 always has ReLU
-                        *reinterpret_cast<uint4*>(obuf + ((q ^ sw) << 4)) =
-                            make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        tma_store_2d(&omap, my_out + (slab_idx & 1) * kEpiSlab, col0, mrow);
-                        tma_store_commit();
-                    }
-                    __syncwarp();
-                    if (j == 0 && a.shift) {
-                        // TemporalShift of the next conv1 (fold 64 of 512 channels): channels 0..63 (unit 0) come from
-                        // segment t+1, channels 64..127 (unit 1) from t-1, zeros at the ends
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const uint32_t up = __shfl_down_sync(0xffffffffu, pk[i], 1);
-                            const uint32_t dn = __shfl_up_sync(0xffffffffu, pk[i], 1);
-                            pk[i] = (u == 0) ? (t_seg < 7 ? up : 0u) : (t_seg > 0 ? dn : 0u);
-                        }
-                    }
-                    // unit u of the chunk -> columns [32u, 32u + 32) of its own buffer: accumulator columns [0, 64) were
-                    // drained by unit 0's loads, which completed before unit 0's store
-                    tmem_st32(tbuf + u * 32, pk);
+                    for (int e = 0; e < 4; ++e) pk[q * 4 + e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);   // conv3 always has ReLU
+                    *cell = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
                 }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&omap, my_slab + slot * kEpiSlab, col0, mrow);
+                    tma_store_commit();
+                }
+                __syncwarp();
+                if (j == 0 && a.shift) {
+                    // TemporalShift of the next conv1 (fold 64 of 512 channels): channels 0..63 (half 0) come from
+                    // segment t+1, channels 64..127 (half 1) from t-1, zeros at the ends
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t up = __shfl_down_sync(0xffffffffu, pk[i], 1);
+                        const uint32_t dn = __shfl_up_sync(0xffffffffu, pk[i], 1);
+                        pk[i] = (half == 0) ? (t_seg < 7 ? up : 0u) : (t_seg > 0 ? dn : 0u);
+                    }
+                }
+                // packed chunk half -> the first 32 of this warp's OWN 64 accumulator columns (already drained); the other
+                // warp of the quarter may still be reading its columns
+                tmem_st32(tbuf, pk);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (elect_one()) mbar_arrive(&y_full[buf]);
+                if (elect_one()) {
+                    mbar_arrive(&y_full[buf]);
+                    tma_store_wait_read1();     // the store of unit n - 1 has finished reading its slab ...
+                }
                 __syncwarp();
+                request(n + 2);                 // ... which is the slab of unit n + 2
             }
-            // ---- second epilogue: z = relu(acc2 + b1'), N2 / 64 units ----
+            // ---- second epilogue: z = relu(acc2 + b1'); this warp's units are cz = half, half + 2, ... ----
             mbar_wait(acc2_full, tile_iter & 1);
             tc_fence_after_sync();
 #pragma unroll 1
-            for (int cz = 0; cz < N2 / 64; ++cz, ++slab_idx) {
-                float4 bb[16];
-                const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) bb[q] = __ldg(bsrc + q);
+            for (int ez = 0; ez < kE2Units; ++ez, ++n) {
+                const int cz = half + 2 * ez;
+                const uint32_t slot = n % 3u;
+                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
                 uint32_t v0[32], v1[32];
                 tmem_ld32(lane_base + 256 + cz * 64, v0);
                 tmem_ld32(lane_base + 256 + cz * 64 + 32, v1);
                 tmem_ld_wait();
-                if (cz == N2 / 64 - 1) {   // the second accumulator is drained: the next tile's M2(0) may overwrite it
+                if (ez == kE2Units - 1) {   // this warp's part of the second accumulator is drained
                     tc_fence_before_sync();
                     __syncwarp();
                     if (elect_one()) mbar_arrive(acc2_empty);
                     __syncwarp();
                 }
-                if (elect_one()) tma_store_wait_read1();
-                __syncwarp();
-                uint8_t* obuf = my_out + (slab_idx & 1) * kEpiSlab + row_off;
+                const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
-                    const float4 b0 = bb[2 * q], b1 = bb[2 * q + 1];
+                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
                     const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
                                         __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
                                         __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
@@ -261,20 +257,22 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
-                    *reinterpret_cast<uint4*>(obuf + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
-                    tma_store_2d(&zmap, my_out + (slab_idx & 1) * kEpiSlab, cz * 64, mrow);
+                    tma_store_2d(&zmap, my_slab + slot * kEpiSlab, cz * 64, mrow);
                     tma_store_commit();
+                    tma_store_wait_read1();
                 }
                 __syncwarp();
+                request(n + 2);
             }
         }
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ==========================================================================================
         // W producer: the ring is filled in the MMA issuer's consumption order
         //   W3(0) W3(1) | W1'(0) W3(2) | W1'(1) W3(3) | ...  (global chunk sequence; W3 chunk index = g % n_chunks)
@@ -319,7 +317,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
             load_w1n(gg);
             if (gg + 2 < total_chunks) load_w3(gg + 2);
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ==========================================================================================
         // MMA issuer
         // ==========================================================================================
@@ -373,7 +371,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                         const uint64_t bdesc = umma_desc_from_lo(sW_lo + ((slot * (uint32_t)kF3WStage + (N2 == 128 ? (uint32_t)kk * 16384u : 0u)) >> 4));
 #pragma unroll
                         for (int k = 0; k < kTileK / 16; ++k)
-                            umma_bf16_ts(d_tmem, ybase + 8 * (kb * 4 + k), bdesc + 2 * k, idesc2, (j | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
+                            umma_bf16_ts(d_tmem, ybase + 64 * kb + 8 * k, bdesc + 2 * k, idesc2, (j | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
                     }
                     umma_commit(&w_empty[slot]);
                     if (s == kStagesPerM2 - 1) {
@@ -393,7 +391,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
         }
     } else {
         // ==========================================================================================
-        // A producer (warp 6): the y2 tile of a 128-row tile = two 3-D boxes {64 channels, 8 segments, 16 pixels}
+        // A producer (warp 10): the y2 tile of a 128-row tile = two 3-D boxes {64 channels, 8 segments, 16 pixels}
         // ==========================================================================================
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
@@ -411,7 +409,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace wd

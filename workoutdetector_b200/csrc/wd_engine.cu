@@ -1439,13 +1439,11 @@ int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
     p.n_chunks = c3.Cout / wd::kF3Chunk;
     p.shift = c1n.fold == 64 ? 1 : 0;
     p.safe_order = e->fuse3_safe;
-    p.w_stages = 3;
-    p.res_depth = 2;
-    // shared memory: 2 A slots (32 KiB each) | W ring | 8 output slabs | residual ring | barriers
+    p.w_stages = 2;
+    // shared memory: 2 A slots (32 KiB each) | W ring | 8 warps x 3 in-place residual / output slabs | barriers
     p.off_w = 2 * 32768;
     p.off_out = p.off_w + p.w_stages * wd::kF3WStage;
-    p.off_res = p.off_out + 8 * wd::kEpiSlab;
-    p.off_bar = p.off_res + 4 * p.res_depth * wd::kEpiSlab;
+    p.off_bar = p.off_out + 8 * 3 * wd::kEpiSlab;
     const size_t smem = (size_t)p.off_bar + 1024 + 1024;
     if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1 (layer 2): %zu bytes of shared memory", smem);
     const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
