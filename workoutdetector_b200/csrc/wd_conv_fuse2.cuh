@@ -384,4 +384,319 @@ conv_fuse2_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], box
     if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// conv_fuse2e_kernel — the residual form of conv_fuse2_kernel with EIGHT epilogue warps (two per scheduler).
+// The four-warp kernel above runs one dependent chain per scheduler: ~0.9 us per 64-column unit whatever the unit does
+// (profiles/r02_op_times: 5 units per tile -> 4.46 us, 6 units -> 5.47 us), which is slower than HBM delivers the tile
+// (layer1.1: 2054 MB at 6.2 TB/s = 331 us against 378 us measured).  Here warps q and q + 4 share TMEM lane quarter q;
+// half 0 owns the y chunks 0 and 2, half 1 the chunks 1 and 3, and the residual is added IN PLACE in the slab the TMA
+// load delivered it to (three 4 KiB slabs per warp, as conv_fuse3_kernel).
+// The packed bf16 tile still has to be compact in columns [0,128) of the accumulator buffer (the second accumulator
+// needs [128, 128 + N2)): packed chunk 1 lands on accumulator columns of chunk 0 and packed chunk 2 on those of chunk 1,
+// i.e. on columns the OTHER warp of the quarter reads in its first unit — the two warps meet on a named barrier (one per
+// quarter) right after their first tcgen05.ld, before either writes anything back.
+// Second epilogue: N2 / 64 units per quarter; with N2 = 64 the two warps of a quarter alternate tiles.
+// Warp roles (352 threads): 0-7 epilogue, 8 W producer, 9 MMA issuer, 10 A producer.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kF2eThreads = 352;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int N2>
+__global__ void __launch_bounds__(kF2eThreads, 1)
+conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], box {64, 256}
+                   const __grid_constant__ CUtensorMap w2map,   // [N2, 256], box {64, N2}
+                   const __grid_constant__ CUtensorMap amap,    // y2 {64, 8, P}
+                   const __grid_constant__ CUtensorMap omap,    // y  [rows, 256], box {64, 32}
+                   const __grid_constant__ CUtensorMap rmap,    // residual, same geometry
+                   const __grid_constant__ CUtensorMap zmap,    // z  [rows, N2],  box {64, 32}
+                   const Fuse2Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sW1 = smem + a.off_w1;
+    uint8_t* sW2 = smem + a.off_w2;
+    uint8_t* sOut = smem + a.off_out;        // 8 warps x 3 slabs x 4 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+    uint64_t* a_full = bars;               // [8]
+    uint64_t* a_empty = bars + 8;          // [8]
+    uint64_t* tmem_full_bar = bars + 16;   // [2]
+    uint64_t* tmem_empty_bar = bars + 18;  // [2]
+    uint64_t* y_full = bars + 20;          // [2]
+    uint64_t* z_full = bars + 22;          // [2]
+    uint64_t* w_bar = bars + 24;           // [1]
+    uint64_t* res_bar = bars + 32;         // [8 warps][3]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 60);
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const int num_tiles = a.num_tiles;
+
+    if (warp == 8) {
+        if (elect_one()) {
+            tma_prefetch_desc(&w1map);
+            tma_prefetch_desc(&w2map);
+            tma_prefetch_desc(&amap);
+            tma_prefetch_desc(&omap);
+            tma_prefetch_desc(&zmap);
+            tma_prefetch_desc(&rmap);
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(&a_full[s], 1);
+                mbar_init(&a_empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], N2 == 128 ? 8 : 4);   // the warps that run the tile's second epilogue
+                mbar_init(&y_full[s], 8);
+                mbar_init(&z_full[s], 1);
+            }
+            mbar_init(w_bar, 1);
+            for (int s = 0; s < 8 * 3; ++s) mbar_init(&res_bar[s], 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    if (warp == 9) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (warp != 8 && warp != 9) pdl_grid_dependency_wait();
+
+    if (warp < 8) {
+        const int quarter = warp & 3, half = warp >> 2;
+        uint8_t* my_slab = sOut + warp * 3 * kEpiSlab;
+        uint64_t* my_res_bar = res_bar + warp * 3;
+        const uint32_t row_off = lane * 128;
+        const uint32_t sw = lane & 7;
+        const int t_seg = lane & 7;
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        // This warp's unit sequence.  Per tile: two y chunks (half 0: 1 then 0, half 1: 2 then 3), then its z units:
+        // N2 = 128: z chunk `half`; N2 = 64: z chunk 0 on the tiles whose iteration parity equals `half`.
+        // A unit is (tile iteration, kind); the slab ring advances on every unit the warp runs.
+        auto y_chunk = [&](int i) { return half + 2 * i; };
+        auto has_z = [&](int ti) { return N2 == 128 || ((ti & 1) == half); };
+        // residual requests run two y units ahead of the consumer; slabs: unit n -> n % 3
+        uint32_t n = 0;                 // units run so far (slab ring position)
+        uint32_t req_ti = 0, req_i = 0, req_n = 0;   // next y unit to request: tile iteration, chunk slot, its ring position
+        uint32_t res_uses[3] = {0, 0, 0};
+        // Request residuals of the not-yet-requested y units whose ring position is <= limit.  The slab of position r is
+        // free once the store of position r - 3 has been read; at the end of unit n (store n committed, wait_group.read 1
+        // done) that holds for every r <= n + 2.
+        auto request_upto = [&](uint32_t limit) {
+            while ((int)req_ti < my_tiles && req_n <= limit) {
+                const int t2 = (int)blockIdx.x + (int)req_ti * (int)gridDim.x;
+                const uint32_t slot = req_n % 3u;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&my_res_bar[slot], kEpiSlab);
+                    tma_load_2d(&rmap, &my_res_bar[slot], my_slab + slot * kEpiSlab, y_chunk((int)req_i) * 64,
+                                t2 * kTileM + quarter * 32);
+                }
+                __syncwarp();
+                ++req_n;
+                if (++req_i == 2) {     // the tile's z unit (if this warp runs it) takes a ring position too
+                    req_i = 0;
+                    if (has_z((int)req_ti)) ++req_n;
+                    ++req_ti;
+                }
+            }
+        };
+        request_upto(2);
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int mrow = tile * kTileM + quarter * 32;
+            const int acc = tile_iter & 1;
+            const uint32_t tacc = lane_base + acc * 256;
+            mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i, ++n) {
+                const int c = y_chunk(i);
+                const uint32_t slot = n % 3u;
+                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tacc + c * 64, v0);
+                tmem_ld32(tacc + c * 64 + 32, v1);
+                const uint32_t uses = slot == 0 ? res_uses[0] : (slot == 1 ? res_uses[1] : res_uses[2]);
+                mbar_wait(&my_res_bar[slot], uses & 1u);
+                if (slot == 0) ++res_uses[0]; else if (slot == 1) ++res_uses[1]; else ++res_uses[2];
+                tmem_ld_wait();
+                // chunks 0 and 1 (this quarter's first units) have left tensor memory: from here on either warp may write
+                // packed columns over the other's accumulator columns
+                if (i == 0) named_bar_sync(1 + quarter, 64);
+                uint32_t pk[32];
+                const float4* bsrc = reinterpret_cast<const float4*>(a.bias1 + c * 64);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
+                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
+                    uint4* cell = reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4));
+                    const uint4 rq = *cell;
+                    float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                  __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                  __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                  __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        f[2 * e] += __uint_as_float(rw[e] << 16);
+                        f[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[q * 4 + e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+                    *cell = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&omap, my_slab + slot * kEpiSlab, c * 64, mrow);
+                    tma_store_commit();
+                }
+                __syncwarp();
+                if (c == 0 && a.shift) {
+                    // TemporalShift of the next conv1 (fold 32 of 256 channels): channels 0..31 from t+1, 32..63 from t-1
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const uint32_t up = __shfl_down_sync(0xffffffffu, pk[k], 1);
+                        const uint32_t dn = __shfl_up_sync(0xffffffffu, pk[16 + k], 1);
+                        pk[k] = t_seg < 7 ? up : 0u;
+                        pk[16 + k] = t_seg > 0 ? dn : 0u;
+                    }
+                }
+                tmem_st32(tacc + c * 32, pk);   // y chunk c -> columns [32c, 32c + 32)
+                if (elect_one()) tma_store_wait_read1();
+                __syncwarp();
+                request_upto(n + 2);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&y_full[acc]);
+            __syncwarp();
+            // ---- second epilogue ----
+            if (has_z(tile_iter)) {
+                const int cz = (N2 == 128) ? half : 0;
+                const uint32_t slot = n % 3u;
+                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
+                mbar_wait(&z_full[acc], (tile_iter >> 1) & 1);
+                tc_fence_after_sync();
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tacc + 128 + cz * 64, v0);
+                tmem_ld32(tacc + 128 + cz * 64 + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                __syncwarp();
+                const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
+                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
+                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+                    *reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&zmap, my_slab + slot * kEpiSlab, cz * 64, mrow);
+                    tma_store_commit();
+                    tma_store_wait_read1();
+                }
+                __syncwarp();
+                request_upto(n + 2);
+                ++n;
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else if (warp == 8) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(w_bar, (uint32_t)a.kblocks * kF2N1 * kTileK * 2 + N2 * kF2K2 * 2);
+            for (int kb = 0; kb < a.kblocks; ++kb) tma_load_2d(&w1map, w_bar, sW1 + kb * kF2N1 * kTileK * 2, kb * kTileK, 0);
+            for (int kb = 0; kb < kF2K2 / kTileK; ++kb) tma_load_2d(&w2map, w_bar, sW2 + kb * N2 * kTileK * 2, kb * kTileK, 0);
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        constexpr uint32_t idesc1 = umma_idesc_bf16(kTileM, kF2N1);
+        constexpr uint32_t idesc2 = umma_idesc_bf16(kTileM, N2);
+        const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
+        const uint32_t sW1_lo = umma_desc_lo(smem_u32(sW1));
+        const uint32_t sW2_lo = umma_desc_lo(smem_u32(sW2));
+        uint32_t ita = 0;
+        int tile_iter = 0;
+        mbar_wait(w_bar, 0);
+        auto second = [&](int ti) {
+            const int acc = ti & 1;
+            mbar_wait(&y_full[acc], (ti >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t ybase = tmem_base + acc * 256;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < kF2K2 / 16; ++k) {
+                    const uint64_t bdesc = umma_desc_from_lo(sW2_lo + (uint32_t)(((k >> 2) * N2 * kTileK * 2) >> 4) + 2 * (k & 3));
+                    umma_bf16_ts(ybase + 128, ybase + 8 * k, bdesc, idesc2, k ? 1u : 0u);
+                }
+                umma_commit(&z_full[acc]);
+            }
+            __syncwarp();
+        };
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int acc = tile_iter & 1;
+            mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kb = 0; kb < a.kblocks; ++kb, ++ita) {
+                const int aslot = ita % a.a_stages;
+                mbar_wait(&a_full[aslot], (ita / a.a_stages) & 1);
+                tc_fence_after_sync();
+                const uint64_t adesc = umma_desc_from_lo(sA_lo + ((uint32_t)(aslot * kATileBytes) >> 4));
+                const uint64_t bdesc = umma_desc_from_lo(sW1_lo + ((uint32_t)(kb * kF2N1 * kTileK * 2) >> 4));
+                if (elect_one()) {
+                    umma_bf16_ss(d_tmem, adesc, bdesc, idesc1, kb ? 1u : 0u);
+#pragma unroll
+                    for (int k = 1; k < kTileK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, 1u);
+                    umma_commit(&a_empty[aslot]);
+                    if (kb == a.kblocks - 1) umma_commit(&tmem_full_bar[acc]);
+                }
+                __syncwarp();
+            }
+            if (tile_iter > 0) second(tile_iter - 1);
+        }
+        if (tile_iter > 0) second(tile_iter - 1);
+    } else {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int px0 = (tile * kTileM) >> 3;
+            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                const int slot = it % a.a_stages;
+                mbar_wait(&a_empty[slot], ((it / a.a_stages) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
+                    tma_load_3d(&amap, &a_full[slot], sA + slot * kATileBytes, kb * kTileK, 0, px0);
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace wd
