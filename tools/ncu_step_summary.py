@@ -22,6 +22,13 @@ for r in rows[hi + 1:]:
     per.setdefault(k, {})[r[idx["Metric Name"]]] = (float(r[idx["Metric Value"]].replace(",", "")), r[idx["Metric Unit"]])
 
 
+# keep the LAST forward only (from its preprocess launch on): the capture may hold warm-up passes and torch's own kernels
+keys = list(per.keys())
+starts = [i for i, k in enumerate(keys) if "preprocess" in k[1]]
+if starts:
+    per = collections.OrderedDict((k, per[k]) for k in keys[starts[-1]:])
+
+
 def tobytes(v, u):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
 
