@@ -369,3 +369,26 @@ def test_fused_layer2_conv3_conv1_equals_unfused(weights, n_clips):
         for nm, t in taps[key].items():
             assert torch.equal(t, taps["01"][nm]), (key, nm, float((t - taps["01"][nm]).abs().max()))
         assert torch.equal(out[key], out["01"]), key
+
+
+# ---------------------------------------------------------------------------------------------------
+# preprocess: the two-columns-per-thread packed-fp32 kernel (product path when the resize does not shrink) against the
+# rows kernel it replaces (WD_PRE_PAIR=0) — same arithmetic and the same fma association per value, so the bf16 frames are bit-identical
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(224, 224), (231, 233), (256, 256), (240, 200)])
+def test_preprocess_pair_kernel_equals_rows_kernel(weights, hw, monkeypatch):
+    import torch
+    from workoutdetector_b200.models import create_model
+    H, W = hw
+    model = create_model(num_class=12, device="cuda")
+    eng = model.engine(8)
+    g = torch.Generator().manual_seed(H * 7 + W)
+    fr = torch.randint(0, 256, (9, H, W, 3), generator=g, dtype=torch.uint8).cuda()
+    idx = torch.tensor([0, 8, 4, -1, 1, 3, 3, 7, 2, 5, 6], dtype=torch.int32).cuda()
+    for in_scale in (1.0 / 255.0, 1.0):
+        monkeypatch.setenv("WD_PRE_PAIR", "1")
+        new = eng.preprocess_u8(fr, idx, in_scale=in_scale).clone()
+        monkeypatch.setenv("WD_PRE_PAIR", "0")
+        old = eng.preprocess_u8(fr, idx, in_scale=in_scale).clone()
+        assert new.shape == old.shape
+        assert torch.equal(new.view(torch.int16), old.view(torch.int16)), (hw, in_scale, float((new.float() - old.float()).abs().max()))

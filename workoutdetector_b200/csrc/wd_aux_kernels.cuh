@@ -299,6 +299,211 @@ __global__ void __launch_bounds__(256) preprocess_u8_rows_kernel(const PreArgs a
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// preprocess_u8_pair_kernel — the product (bf16) path when the resize does not shrink (scale <= 1, e.g. the
+// 224 -> 256 -> crop 224 of the headline workload).  ncu on the rows kernel above (profiles/r02_ncu_full_top_kernels.txt):
+// issue slots 85 % busy, 1014 executed instructions per thread — the fully unrolled, predicated row loop computes all
+// 16 candidate source-row blends per thread.  Here:
+//   * one thread owns TWO adjacent output columns for kPairRows rows: with scale <= 1 their four horizontal taps are
+//     three consecutive source pixels, converted once (PRMT under the exponent of 2^23, then packed fp32 arithmetic:
+//     add/mul/fma.f32x2 — two lanes per issue slot, each lane IEEE-rounded exactly like the scalar instruction);
+//   * the row loop is a real loop with warp-uniform branches: a source row's horizontal blend is computed once and
+//     carried to the next output row (9-10 blends per 8 rows);
+//   * the vertical taps (y0, y1, ly) of the CTA's rows come from a small shared-memory table;
+//   * each thread stores both pixels with one 128-bit store (a warp writes 512 contiguous bytes).
+// The arithmetic per value is the one of the kernels above: ((b*in_scale)*(1-lx) + (b'*in_scale)*lx) blended
+// vertically the same way, then (v - mean) * (1/std).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairRows = 8;      // output rows per thread
+constexpr int kPairGroups = 2;    // row groups per CTA (256 threads = 2 x 128 column-pair threads)
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+__global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArgs a, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t srow[];
+    __shared__ float4 ytab[kPairRows * kPairGroups];   // {y0 - ya, y1 - ya, ly, -} per output row of the CTA
+    constexpr int kRows = kPairRows * kPairGroups;
+    const int oy0 = blockIdx.x * kRows;
+    const int f = blockIdx.y;
+    const int src = a.src_index ? a.src_index[f] : f;
+    const int tid = threadIdx.x;
+    const int group = tid >> 7;
+    const int col = (tid & 127) * 2;
+    const int ox = col - a.pad;                        // pad is even: both columns are inside the image or both outside
+    const bool active = col < a.pitch;
+    const bool inside = (unsigned)ox < 224u;
+    __nv_bfloat16* o = out + (((size_t)f * 224 + oy0 + group * kPairRows) * a.pitch + col) * 4;
+    const size_t orow = (size_t)a.pitch * 4;
+    if (src < 0) {  // zero raw frame: (0*in_scale - mean) / std
+        if (active) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(-a.mean[0] / a.stdv[0], -a.mean[1] / a.stdv[1]);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(-a.mean[2] / a.stdv[2], 0.0f);
+            const uint32_t w0 = inside ? *reinterpret_cast<const uint32_t*>(&lo) : 0u;
+            const uint32_t w1 = inside ? *reinterpret_cast<const uint32_t*>(&hi) : 0u;
+#pragma unroll
+            for (int r = 0; r < kPairRows; ++r) *reinterpret_cast<uint4*>(o + r * orow) = make_uint4(w0, w1, w0, w1);
+        }
+        return;
+    }
+    auto src_y = [&](int oy, int& y0, int& y1, float& ly) {
+        float sy = a.scale_y * ((float)(oy + a.top) + 0.5f) - 0.5f;
+        sy = sy < 0.0f ? 0.0f : sy;
+        y0 = min((int)sy, a.H - 1);
+        y1 = min(y0 + 1, a.H - 1);
+        ly = sy - (float)y0;
+    };
+    int ya, yb, yt;
+    float lt;
+    src_y(oy0, ya, yt, lt);
+    src_y(oy0 + kRows - 1, yt, yb, lt);
+    if (tid < kRows) {
+        int y0, y1;
+        float ly;
+        src_y(oy0 + tid, y0, y1, ly);
+        ytab[tid] = make_float4(__int_as_float(y0 - ya), __int_as_float(y1 - ya), ly, 0.0f);
+    }
+    const uint32_t row_b = (uint32_t)a.W * 3u;
+    const size_t span_begin = ((size_t)src * a.H + ya) * row_b;
+    const size_t span_end = ((size_t)src * a.H + yb + 1) * row_b;  // exclusive
+    const size_t abegin = span_begin & ~(size_t)15;
+    const uint32_t shift = (uint32_t)(span_begin - abegin);
+    const int nvec = (int)((span_end - abegin + 15) >> 4);
+    // stage the span with cp.async (no register round trip); the tap set-up below runs while the bytes are in flight.
+    // The last vector may reach past the end of the allocation: it is copied with a byte count (zero fill).
+    const uint32_t srow_s = smem_u32(srow);
+    for (int v = tid; v < nvec; v += 256) {
+        const size_t g = abegin + (size_t)v * 16;
+        const uint32_t nb = g + 16 <= a.total_bytes ? 16u : (uint32_t)(a.total_bytes - g);
+        cp_async_16(srow_s + (uint32_t)v * 16u, a.frames + g, nb);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // horizontal taps of the two columns
+    float sxa = a.scale_x * ((float)(ox + a.left) + 0.5f) - 0.5f;
+    float sxb = a.scale_x * ((float)(ox + 1 + a.left) + 0.5f) - 0.5f;
+    sxa = sxa < 0.0f ? 0.0f : sxa;
+    sxb = sxb < 0.0f ? 0.0f : sxb;
+    const int x0a = min((int)sxa, a.W - 1), x0b = min((int)sxb, a.W - 1);
+    const float lxa = sxa - (float)x0a, lxb = sxb - (float)x0b;
+    // three source pixels p0 = x0a, p1, p2 (clamped at the right edge) carry all four taps: column a blends (p0, p1);
+    // column b blends (p0, p1) when x0b == x0a, else (p1, p2).  Column b is written as a three-term sum with a zero
+    // weight on the unused pixel, which rounds exactly like the two-term blend (x*0 = 0, fma(x, 0, t) = t).
+    const uint32_t off0 = shift + (uint32_t)x0a * 3u;
+    const uint32_t off1 = shift + (uint32_t)min(x0a + 1, a.W - 1) * 3u;
+    const uint32_t off2 = shift + (uint32_t)min(x0a + 2, a.W - 1) * 3u;
+    const bool same = x0b == x0a;
+    const float wa0 = 1.0f - lxa, wa1 = lxa;
+    const float wb0 = same ? 1.0f - lxb : 0.0f, wb1 = same ? lxb : 1.0f - lxb, wb2 = same ? 0.0f : lxb;
+    const uint64_t WA0 = f2_pack(wa0, wa0), WA1 = f2_pack(wa1, wa1);
+    const uint64_t WB0 = f2_pack(wb0, wb0), WB1 = f2_pack(wb1, wb1), WB2 = f2_pack(wb2, wb2);
+    const uint64_t KNEG = f2_pack(-8388608.0f, -8388608.0f), KS = f2_pack(a.in_scale, a.in_scale);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(srow);
+    auto bytes3 = [&](uint32_t byte_off) -> uint32_t {   // three consecutive bytes at any alignment, in the low 24 bits
+        const uint32_t* w = sw + (byte_off >> 2);
+        return __funnelshift_r(w[0], w[1], (byte_off & 3u) * 8u);
+    };
+    // horizontal blend of source row (ya + yrel) at both columns: A01 = column a channels (0,1), B01 = column b channels
+    // (0,1), C2 = (a.c2, b.c2)
+    auto hrow = [&](int yrel, uint64_t& A01, uint64_t& B01, uint64_t& C2) {
+        const uint32_t ro = (uint32_t)yrel * row_b;
+        const uint32_t x0 = bytes3(ro + off0), x1 = bytes3(ro + off1), x2 = bytes3(ro + off2);
+        // uint8 -> float: PRMT the byte under the exponent of 2^23, subtract 2^23 (exact), scale
+        uint64_t p0 = f2_pack(__uint_as_float(__byte_perm(x0, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x0, 0x4B000000u, 0x7651)));
+        uint64_t p1 = f2_pack(__uint_as_float(__byte_perm(x1, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x1, 0x4B000000u, 0x7651)));
+        uint64_t p2 = f2_pack(__uint_as_float(__byte_perm(x2, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x2, 0x4B000000u, 0x7651)));
+        uint64_t q01 = f2_pack(__uint_as_float(__byte_perm(x0, 0x4B000000u, 0x7652)), __uint_as_float(__byte_perm(x1, 0x4B000000u, 0x7652)));
+        uint64_t q2 = f2_pack(__uint_as_float(__byte_perm(x2, 0x4B000000u, 0x7652)), 8388608.0f);
+        p0 = f2_mul(f2_add(p0, KNEG), KS);
+        p1 = f2_mul(f2_add(p1, KNEG), KS);
+        p2 = f2_mul(f2_add(p2, KNEG), KS);
+        q01 = f2_mul(f2_add(q01, KNEG), KS);
+        q2 = f2_mul(f2_add(q2, KNEG), KS);
+        // a*b + c*d is contracted as fma(a, b, round(c*d)) by nvcc (the kernels above) and by ATen's CPU code alike
+        A01 = f2_fma(p0, WA0, f2_mul(p1, WA1));
+        B01 = f2_fma(p0, WB0, f2_fma(p1, WB1, f2_mul(p2, WB2)));
+        float c0, c1, c2, cx;
+        f2_unpack(q01, c0, c1);
+        f2_unpack(q2, c2, cx);
+        const float a2 = __fmaf_rn(c0, wa0, __fmul_rn(c1, wa1));
+        const float b2 = __fmaf_rn(c0, wb0, __fmaf_rn(c1, wb1, __fmul_rn(c2, wb2)));
+        C2 = f2_pack(a2, b2);
+    };
+    const float rs0 = 1.0f / a.stdv[0], rs1 = 1.0f / a.stdv[1], rs2 = 1.0f / a.stdv[2];
+    const uint64_t NM01 = f2_pack(-a.mean[0], -a.mean[1]), NM2 = f2_pack(-a.mean[2], -a.mean[2]);
+    const uint64_t RS01 = f2_pack(rs0, rs1), RS2 = f2_pack(rs2, rs2);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!active) return;
+    if (!inside) {
+#pragma unroll
+        for (int r = 0; r < kPairRows; ++r) *reinterpret_cast<uint4*>(o + r * orow) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    int py0 = -1, py1 = -1;                     // source rows (relative) the carried blends belong to
+    uint64_t tA = 0, tB = 0, tC = 0, bA = 0, bB = 0, bC = 0;
+#pragma unroll 1
+    for (int r = 0; r < kPairRows; ++r) {
+        const float4 yt4 = ytab[group * kPairRows + r];
+        const int y0 = __float_as_int(yt4.x), y1 = __float_as_int(yt4.y);
+        const float ly = yt4.z;
+        // warp-uniform reuse of the carried blends (up-scaling: y0 advances by 0 or 1 per output row)
+        if (y0 != py0) {
+            if (y0 == py1) {
+                tA = bA; tB = bB; tC = bC;
+            } else {
+                hrow(y0, tA, tB, tC);
+            }
+            py0 = y0;
+            py1 = -1;
+        }
+        if (y1 != py1) {
+            if (y1 == y0) {
+                bA = tA; bB = tB; bC = tC;
+            } else {
+                hrow(y1, bA, bB, bC);
+            }
+            py1 = y1;
+        }
+        const uint64_t W0 = f2_pack(1.0f - ly, 1.0f - ly), W1 = f2_pack(ly, ly);
+        uint64_t vA = f2_fma(tA, W0, f2_mul(bA, W1));
+        uint64_t vB = f2_fma(tB, W0, f2_mul(bB, W1));
+        uint64_t vC = f2_fma(tC, W0, f2_mul(bC, W1));
+        vA = f2_mul(f2_add(vA, NM01), RS01);
+        vB = f2_mul(f2_add(vB, NM01), RS01);
+        vC = f2_mul(f2_add(vC, NM2), RS2);
+        float a0, a1, b0, b1, a2, b2;
+        f2_unpack(vA, a0, a1);
+        f2_unpack(vB, b0, b1);
+        f2_unpack(vC, a2, b2);
+        const __nv_bfloat162 pa0 = __floats2bfloat162_rn(a0, a1), pa1 = __floats2bfloat162_rn(a2, 0.0f);
+        const __nv_bfloat162 pb0 = __floats2bfloat162_rn(b0, b1), pb1 = __floats2bfloat162_rn(b2, 0.0f);
+        *reinterpret_cast<uint4*>(o + r * orow) =
+            make_uint4(*reinterpret_cast<const uint32_t*>(&pa0), *reinterpret_cast<const uint32_t*>(&pa1),
+                       *reinterpret_cast<const uint32_t*>(&pb0), *reinterpret_cast<const uint32_t*>(&pb1));
+    }
+}
+
 // [F,3,224,224] float (already normalised, what the reference nn.Module takes: tsm.py:409) -> [F,224,pitch,4];
 // columns outside [pad, pad+224) are written as zeros.
 template <typename OutT>

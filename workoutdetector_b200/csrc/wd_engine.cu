@@ -1721,7 +1721,16 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     // rows of the source a band of kPreRows output rows can touch (+2 for the bilinear neighbour and rounding)
     const size_t band_rows = (size_t)std::ceil(wd::kPreRows * a.scale_y) + 2;
     const size_t smem_rows = band_rows * W * 3 + 64;  // + alignment shift, 16-byte rounding and the word over-read
-    if (smem_rows <= 40 * 1024) {
+    // product path without shrinking (the headline 224 -> 256 -> crop 224): two columns per thread, packed fp32
+    const size_t band_pair = (size_t)std::ceil(wd::kPairRows * wd::kPairGroups * a.scale_y) + 2;
+    const size_t smem_pair = band_pair * W * 3 + 64;
+    const char* pair_env = getenv("WD_PRE_PAIR");   // 0: the rows kernel (differential tests)
+    const bool pair_off = pair_env && atoi(pair_env) == 0;
+    if (!f32 && !pair_off && a.scale_x <= 1.0f && a.scale_y <= 1.0f && (a.pad & 1) == 0 && (a.pitch & 1) == 0 &&
+        a.pitch <= 256 && smem_pair <= 40 * 1024) {
+        dim3 grid(224 / (wd::kPairRows * wd::kPairGroups), n_out);
+        wd::preprocess_u8_pair_kernel<<<grid, 256, smem_pair, st>>>(a, static_cast<__nv_bfloat16*>(out));
+    } else if (smem_rows <= 40 * 1024) {
         dim3 grid(224 / wd::kPreRows, n_out);
         if (f32)
             wd::preprocess_u8_rows_kernel<float><<<grid, 256, smem_rows, st>>>(a, static_cast<float*>(out));
