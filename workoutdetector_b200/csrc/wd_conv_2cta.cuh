@@ -444,16 +444,27 @@ struct Conv2CtaStripArgs {
     int tiles_w;       // W / 14
     int w_stages;      // W ring depth
     int w_resident;    // w_stages == 9 * cin_blocks: every tap's W half is loaded once and stays (layer 1, Cin = 64)
-    int off_w, off_out, off_bar;  // byte offsets (A ring of two kStripStage stages at 0)
+    int num_rows7;     // W7: clips * 7 (clip, h) rows; a strip is two of them
+    int off_w, off_out, off_bar;  // byte offsets (A ring of two stages of three tap rows at 0)
 };
 
-template <int BN>
+// W7 = true: 7 x 7 images (layer 4).  A 14-pixel strip would be two image rows, so the CTA's tile is two consecutive
+// (clip, h) rows q0 = 2 * strip and q0 + 1 (the next image's row 0 after an image's row 6), each loaded as its own
+// 9-pixel box x = -1 .. 7 (zero fill left and right) for each of the three input rows h - 1 .. h + 1 (zero fill above and
+// below): a tap-row buffer is [9 slots of sub-row A | 9 slots of sub-row B] = 18 KiB, tap (dh, dw) starts at slot dw of
+// buffer dh.  Accumulator rows 0..55 are sub-row A, 72..127 sub-row B (slots 7 and 8 are dead); the 112 output rows
+// are contiguous in the [rows, C] output, so warps 0 / 3 store 32 rows, warps 1 / 2 store 24 (`omap16` is then the
+// 24-row map; warp 2 stores from row 8 of its slab).  One box per (tap row, sub-row, channel block) instead of tap
+// mode's one box per (tap, sub-row, channel block): a third of the A fill traffic through shared memory.
+template <int BN, bool W7 = false>
 __global__ void __launch_bounds__(288, 1)
 conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
                        const Conv2CtaStripArgs a) {
     constexpr int kWHalf = (BN / 2) * kTileK * 2;  // this CTA's half of one tap's W tile
     constexpr int kAStages = 2;
+    constexpr int kRowBuf = W7 ? 18 * 1024 : 16384;   // one tap row of the A stage
+    constexpr int kAStage = 3 * kRowBuf;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
@@ -528,8 +539,10 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         int tile_iter = 0;
         for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
             const int strip = strip_of(tile);
-            const bool live = strip < a.num_strips;
-            const int mrow = strip * kStripRows + warp * 32;  // strips are consecutive 112-row groups of the output
+            // W7: sub-row A (warps 0, 1) is live when 2 * strip < rows, sub-row B (warps 2, 3) when 2 * strip + 1 < rows
+            const bool live = W7 ? (2 * strip + (warp >> 1) < a.num_rows7) : (strip < a.num_strips);
+            // strips are consecutive 112-row groups of the output
+            const int mrow = strip * kStripRows + (W7 ? (warp == 0 ? 0 : warp == 1 ? 32 : warp == 2 ? 56 : 80) : warp * 32);
             const int acc = tile_iter & 1;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN;
             const uint32_t leader_empty = mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0);
@@ -576,8 +589,15 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                 __syncwarp();
                 if (elect_one()) {
                     if (live) {
-                        if (warp == 3) tma_store_2d(&omap16, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
-                        else tma_store_2d(&omap, my_out + (chunk_idx & 1) * kEpiSlab, cta_n0 + c * 64, mrow);
+                        const uint8_t* src = my_out + (chunk_idx & 1) * kEpiSlab;
+                        if (W7) {
+                            if (warp == 1) tma_store_2d(&omap16, src, cta_n0 + c * 64, mrow);               // slots 4..6
+                            else if (warp == 2) tma_store_2d(&omap16, src + 1024, cta_n0 + c * 64, mrow);   // slots 9..11
+                            else tma_store_2d(&omap, src, cta_n0 + c * 64, mrow);
+                        } else {
+                            if (warp == 3) tma_store_2d(&omap16, src, cta_n0 + c * 64, mrow);
+                            else tma_store_2d(&omap, src, cta_n0 + c * 64, mrow);
+                        }
                     }
                     tma_store_commit();
                 }
@@ -623,7 +643,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                     const int aslot = ita % kAStages;
                     mbar_wait(&a_full[aslot], (ita / kAStages) & 1);
                     tc_fence_after_sync();
-                    const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * kStripStage) >> 4);
+                    const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * kAStage) >> 4);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap, ++itw) {
                         const int wslot = itw % a.w_stages;
@@ -632,7 +652,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                             tc_fence_after_sync();
                         }
                         const uint64_t adesc =
-                            umma_desc_from_lo(a_lo + (uint32_t)((tap / 3) * (16384 >> 4) + (tap % 3) * (1024 >> 4)));
+                            umma_desc_from_lo(a_lo + (uint32_t)((tap / 3) * (kRowBuf >> 4) + (tap % 3) * (1024 >> 4)));
                         const uint64_t bdesc = umma_desc_from_lo(sW_lo + ((uint32_t)(wslot * kWHalf) >> 4));
                         const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
                         if (elect_one()) {
@@ -657,18 +677,24 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         uint32_t it = 0;
         for (int tile = pair; tile < a.num_tiles; tile += npairs) {
             const int strip = strip_of(tile);
-            const int ws = strip % a.tiles_w;
-            const int q = strip / a.tiles_w;
+            const int ws = W7 ? 0 : strip % a.tiles_w;
+            const int q = W7 ? 2 * strip : strip / a.tiles_w;
             const int h = q % a.Hout;
             const int n = q / a.Hout;  // past-the-end strips have n >= clips: the whole box is out of bounds -> zeros
+            const int hb = (q + 1) % a.Hout, nb = (q + 1) / a.Hout;   // W7: sub-row B
             for (int cb = 0; cb < a.cin_blocks; ++cb, ++it) {
                 const int slot = it % kAStages;
                 mbar_wait(&a_empty[slot], ((it / kAStages) & 1) ^ 1);
                 const uint32_t leader_full = mapa_shared(smem_u32(&a_full[slot]), 0);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx_cluster(leader_full, 16384);
-                    tma_load_5d_2cta(&amap, leader_full, sA + slot * kStripStage + prow * 16384, cb * kTileK, 0,
-                                     ws * kStripPixels - 1, h - 1 + prow, n);
+                    mbar_arrive_expect_tx_cluster(leader_full, kRowBuf);
+                    uint8_t* dst = sA + slot * kAStage + prow * kRowBuf;
+                    if (W7) {
+                        tma_load_5d_2cta(&amap, leader_full, dst, cb * kTileK, 0, -1, h - 1 + prow, n);
+                        tma_load_5d_2cta(&amap, leader_full, dst + 9 * 1024, cb * kTileK, 0, -1, hb - 1 + prow, nb);
+                    } else {
+                        tma_load_5d_2cta(&amap, leader_full, dst, cb * kTileK, 0, ws * kStripPixels - 1, h - 1 + prow, n);
+                    }
                 }
                 __syncwarp();
             }

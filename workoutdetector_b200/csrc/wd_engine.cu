@@ -166,6 +166,8 @@ struct ConvLayer {
     CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
     CUtensorMap amap_s2; // stride-2 3x3 (conv_strip2d_kernel): contiguous 16-pixel row boxes of the INPUT {C, T, W, H, clips}
     CUtensorMap omap24;  // output, box {64, 24}
+    CUtensorMap amap9;   // 7 x 7 strip mode: {C, T, W, H, clips} view, box {64, 8, 9, 1, 1}
+    bool has_strip7 = false;   // 3x3 stride-1 convolution on 7 x 7 images: conv_2cta_strip_kernel<256, true>
     bool has_s2 = false;
 };
 
@@ -1041,6 +1043,57 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     return WD_OK;
 }
 
+// 3x3 stride-1 convolutions on 7 x 7 images (layer4.1 / layer4.2 conv2): the pair strip kernel with two image rows per
+// CTA tile (conv_2cta_strip_kernel<256, true>) instead of tap boxes.  WD_STRIP7=0 keeps the tap-mode pair kernel.
+int g_strip7 = getenv("WD_STRIP7") ? atoi(getenv("WD_STRIP7")) : 1;
+int launch_2cta_strip7(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    constexpr int BN = 256;
+    static bool configured = false;
+    auto kfn = wd::conv_2cta_strip_kernel<BN, true>;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Conv2CtaStripArgs p{};
+    p.bias = a.bias;
+    p.Hout = a.Hout;
+    p.Wout = a.Wout;
+    p.cin_blocks = a.cin_blocks;
+    p.relu = a.relu;
+    p.n_tiles = c.Cout / BN;
+    p.tiles_w = 1;
+    p.num_rows7 = a.M / 56;                       // (clip, h) rows of 7 pixels x 8 segments
+    p.num_strips = (p.num_rows7 + 1) / 2;
+    p.num_tiles = ((p.num_strips + 1) / 2) * p.n_tiles;
+    const int whalf = (BN / 2) * 128;
+    const int a_stage = 3 * 18 * 1024;
+    const int fixed = 2 * a_stage + 8 * wd::kEpiSlab + 2048 + 1024;
+    p.w_stages = std::min(8, (232448 - fixed) / whalf);
+    p.w_resident = 0;
+    p.off_w = 2 * a_stage;
+    p.off_out = p.off_w + p.w_stages * whalf;
+    p.off_bar = p.off_out + 8 * wd::kEpiSlab;
+    const int total = p.off_bar + 2048 + 1024;
+    int pairs = std::min(p.num_tiles, sm_count / 2);
+    pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(288);
+    cfg.dynamicSmemBytes = total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap9, c.omap, c.omap24, p));
+    return WD_OK;
+}
+
 int g_strip2 = getenv("WD_STRIP2") ? atoi(getenv("WD_STRIP2")) : 3;  // two output rows per tile: 1 = the 64 -> 64 3x3 convolutions, 2 = + the 128-wide ones, 3 = + the stride-2 3x3 of layer 2
 
 // 3x3 stride 1, 64 -> 64 channels (layer-1 conv2): two output rows per tile, N = 128 MMAs for the shared input rows
@@ -1126,6 +1179,7 @@ int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
     if (g_strip2 && c.a_mode == wd::A_STRIP && c.tile_n == 64 && c.Cin == 64 && c.Cout == 64 && a.residual == nullptr &&
         a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
         return launch_strip2(c, a, sm_count, st);
+    if (g_strip7 && g_2cta >= 3 && c.has_strip7 && a.residual == nullptr && a.fold == 0) return launch_2cta_strip7(c, a, sm_count, st);
     if (eligible_2cta(c, a)) return launch_2cta(c, a, sm_count, st);
     if (g_2cta >= 5 && c.a_mode == wd::A_STRIP && a.residual == nullptr && c.tile_n == 64)
         return launch_2cta_strip<64>(c, a, sm_count, st);  // narrow tiles on a CTA pair: 256 x 64 per instruction
@@ -1311,6 +1365,15 @@ int make_amap5(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t
     const uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16, (uint64_t)W * Cin * 16,
                                  (uint64_t)H * W * Cin * 16};
     const uint32_t box[5] = {64, 8, 16, 1, 1};
+    return make_tmap_bf16(map, base, 5, dims, strides, box);
+}
+
+// 7 x 7 strip mode: the same 5-D view with a 9-pixel box (x = -1 .. 7 of one image row).
+int make_amap9(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t clips) {
+    const uint64_t dims[5] = {(uint64_t)Cin, 8, (uint64_t)W, (uint64_t)H, (uint64_t)clips};
+    const uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16, (uint64_t)W * Cin * 16,
+                                 (uint64_t)H * W * Cin * 16};
+    const uint32_t box[5] = {64, 8, 9, 1, 1};
     return make_tmap_bf16(map, base, 5, dims, strides, box);
 }
 
@@ -2013,6 +2076,12 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
                 WD_TRY(make_amap_tap(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips, c.stride,
                                      c.Wout == 7 ? 7 : wd::kStripPixels));
+                if (c.k == 3 && c.stride == 1 && c.Wout == 7 && c.Hout == 7 && c.tile_n == 256 && c.Cout % 256 == 0 &&
+                    c.Cin % 64 == 0 && c.fold == 0 && o.res_buf < 0) {   // layer4.1 / layer4.2 conv2
+                    WD_TRY(make_amap9(&c.amap9, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
+                    WD_TRY(make_omap(&c.omap24, e->buf[o.out_buf], c.Cout, rows, 24));
+                    c.has_strip7 = true;
+                }
                 if (o.in2_buf >= 0) {  // fused stride-2 downsample: the block input at twice the resolution
                     const ConvLayer& d = e->convs[c.fuse_ds];
                     WD_TRY(make_amap_tap(&c.amap32, e->buf[o.in2_buf], d.Cin, d.Win, d.Hin, (size_t)e->desc.max_clips,
@@ -2456,6 +2525,12 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
         if (c.a_mode == wd::A_TAP) {
             rc = make_amap_tap(&c.amap, x, Cin, Win, Hin, (size_t)clips, stride, c.Wout == 7 ? 7 : wd::kStripPixels);
             if (rc == WD_OK) rc = make_omap(&c.omap16, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 16);
+            if (rc == WD_OK && ksize == 3 && stride == 1 && c.Wout == 7 && c.Hout == 7 && c.tile_n == 256 && Cout % 256 == 0 &&
+                Cin % 64 == 0 && fold == 0 && !residual) {
+                rc = make_amap9(&c.amap9, x, Cin, Win, Hin, (size_t)clips);
+                if (rc == WD_OK) rc = make_omap(&c.omap24, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 24);
+                c.has_strip7 = rc == WD_OK;
+            }
         }
         if (c.a_mode == wd::A_STRIP) {
             rc = make_amap5(&c.amap, x, Cin, Win, Hin, (size_t)clips);
