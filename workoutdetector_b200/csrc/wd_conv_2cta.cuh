@@ -445,6 +445,11 @@ struct Conv2CtaStripArgs {
     int w_stages;      // W ring depth
     int w_resident;    // w_stages == 9 * cin_blocks: every tap's W half is loaded once and stays (layer 1, Cin = 64)
     int num_rows7;     // W7: clips * 7 (clip, h) rows; a strip is two of them
+    // Tail split: the tiles of the last, partial wave (num_tiles % pairs of them) are cut into `split` column slices of
+    // BN / split columns each, so that up to `split` times as many pairs share that wave (224 tiles on 74 pairs are
+    // 3.03 waves: the two left-over tiles become eight 64-column ones).  full_tiles = tiles in complete waves (a
+    // multiple of the pair count), tail_sub = left-over tiles x split.  split = 1: the plain schedule.
+    int full_tiles, tail_sub, split;
     int off_w, off_out, off_bar;  // byte offsets (A ring of two stages of three tap rows at 0)
 };
 
@@ -527,18 +532,35 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
     // this CTA's strip of pair tile `tile` (may be past the end for the peer of the last tile: loads are zero-filled
     // by TMA, stores are skipped)
     auto strip_of = [&](int tile) { return (tile / a.n_tiles) * 2 + (int)rank; };
+    // work item `w` (= pair + round * pairs) -> tile, first output column, columns
+    auto work_of = [&](int w, int& tile, int& n0, int& nc) -> bool {
+        if (w < a.full_tiles) {
+            tile = w;
+            n0 = cta_n0;
+            nc = BN;
+            return true;
+        }
+        const int u = w - a.full_tiles;
+        if (u >= a.tail_sub) return false;
+        tile = a.full_tiles + u / a.split;
+        nc = BN / a.split;
+        n0 = (tile % a.n_tiles) * BN + (u % a.split) * nc;
+        return true;
+    };
 
     if (warp < 4) {
         // ============================== epilogue: 112 rows x BN columns ==============================
         uint8_t* my_out = sOut + warp * 2 * kEpiSlab;
         const uint32_t row_off = lane * 128;
         const uint32_t sw = lane & 7;
-        constexpr int kChunks = BN / 64;
         const bool relu = a.relu != 0;
         uint32_t chunk_idx = 0;
         int tile_iter = 0;
-        for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
+        int tile, n0, nc;
+        for (int w = pair; work_of(w, tile, n0, nc); w += npairs, ++tile_iter) {
             const int strip = strip_of(tile);
+            const int chunks = nc >> 6;
+            const float* bias_src = (n0 == cta_n0) ? sBias : a.bias + n0;   // tail slices of another n-tile: from global
             // W7: sub-row A (warps 0, 1) is live when 2 * strip < rows, sub-row B (warps 2, 3) when 2 * strip + 1 < rows
             const bool live = W7 ? (2 * strip + (warp >> 1) < a.num_rows7) : (strip < a.num_strips);
             // strips are consecutive 112-row groups of the output
@@ -549,16 +571,16 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
             mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
             tc_fence_after_sync();
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c, ++chunk_idx) {
+            for (int c = 0; c < chunks; ++c, ++chunk_idx) {
                 float4 bb[16];
-                const float4* bsrc = reinterpret_cast<const float4*>(sBias + c * 64);
+                const float4* bsrc = reinterpret_cast<const float4*>(bias_src + c * 64);
 #pragma unroll
                 for (int u = 0; u < 16; ++u) bb[u] = bsrc[u];
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr + c * 64, v0);
                 tmem_ld32(taddr + c * 64 + 32, v1);
                 tmem_ld_wait();
-                if (c == kChunks - 1) {
+                if (c == chunks - 1) {
                     tc_fence_before_sync();
                     __syncwarp();
                     if (elect_one()) mbar_arrive_cluster(leader_empty);
@@ -591,12 +613,12 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                     if (live) {
                         const uint8_t* src = my_out + (chunk_idx & 1) * kEpiSlab;
                         if (W7) {
-                            if (warp == 1) tma_store_2d(&omap16, src, cta_n0 + c * 64, mrow);               // slots 4..6
-                            else if (warp == 2) tma_store_2d(&omap16, src + 1024, cta_n0 + c * 64, mrow);   // slots 9..11
-                            else tma_store_2d(&omap, src, cta_n0 + c * 64, mrow);
+                            if (warp == 1) tma_store_2d(&omap16, src, n0 + c * 64, mrow);               // slots 4..6
+                            else if (warp == 2) tma_store_2d(&omap16, src + 1024, n0 + c * 64, mrow);   // slots 9..11
+                            else tma_store_2d(&omap, src, n0 + c * 64, mrow);
                         } else {
-                            if (warp == 3) tma_store_2d(&omap16, src, cta_n0 + c * 64, mrow);
-                            else tma_store_2d(&omap, src, cta_n0 + c * 64, mrow);
+                            if (warp == 3) tma_store_2d(&omap16, src, n0 + c * 64, mrow);
+                            else tma_store_2d(&omap, src, n0 + c * 64, mrow);
                         }
                     }
                     tma_store_commit();
@@ -609,8 +631,11 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
     } else if (warp == 4) {
         // ============================== W producer: this CTA's half of every tap ==============================
         uint32_t it = 0;
-        for (int tile = pair; tile < a.num_tiles; tile += npairs) {
-            if (a.w_resident && tile != pair) break;  // all taps were loaded with the first tile and stay
+        int tile, n0, nc;
+        for (int w = pair; work_of(w, tile, n0, nc); w += npairs) {
+            if (a.w_resident && w != pair) break;  // all taps were loaded with the first tile and stay (split == 1)
+            // a slice of nc columns: this CTA's nc / 2 rows are the first rows of the (fixed-size) box it loads
+            const int wrow = n0 + (int)rank * (nc / 2);
             for (int cb = 0; cb < a.cin_blocks; ++cb) {
                 for (int tap = 0; tap < 9; ++tap, ++it) {
                     const int slot = it % a.w_stages;
@@ -619,8 +644,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                     if (elect_one()) {
                         if (rank == 0) mbar_arrive_expect_tx_cluster(leader_full, 2 * kWHalf);
                         else mbar_arrive_cluster(leader_full);
-                        tma_load_2d_2cta(&wmap_half, leader_full, sW + slot * kWHalf, (tap * a.cin_blocks + cb) * kTileK,
-                                         cta_n0 + (int)rank * (BN / 2));
+                        tma_load_2d_2cta(&wmap_half, leader_full, sW + slot * kWHalf, (tap * a.cin_blocks + cb) * kTileK, wrow);
                     }
                     __syncwarp();
                 }
@@ -629,12 +653,13 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
     } else if (warp == 5) {
         // ============================== MMA issuer (leader) ==============================
         if (rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
             const uint32_t sA_lo = umma_desc_lo(smem_u32(sA));
             const uint32_t sW_lo = umma_desc_lo(smem_u32(sW));
             uint32_t ita = 0, itw = 0;
             int tile_iter = 0;
-            for (int tile = pair; tile < a.num_tiles; tile += npairs, ++tile_iter) {
+            int tile, n0, nc;
+            for (int w = pair; work_of(w, tile, n0, nc); w += npairs, ++tile_iter) {
+                const uint32_t idesc = umma_idesc_bf16(256, (uint32_t)nc);
                 const int acc = tile_iter & 1;
                 mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
@@ -675,7 +700,8 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         // ============================== A producers: warp 6 + r loads input row h-1+r ==============================
         const int prow = warp - 6;
         uint32_t it = 0;
-        for (int tile = pair; tile < a.num_tiles; tile += npairs) {
+        int tile, n0, nc;
+        for (int w = pair; work_of(w, tile, n0, nc); w += npairs) {
             const int strip = strip_of(tile);
             const int ws = W7 ? 0 : strip % a.tiles_w;
             const int q = W7 ? 2 * strip : strip / a.tiles_w;

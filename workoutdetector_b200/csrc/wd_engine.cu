@@ -992,6 +992,20 @@ int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
                                  : launch_2cta_t<256, false, false>(c, a, sm_count, st);
 }
 
+// Tail split of the pair strip kernel (Conv2CtaStripArgs): the tiles of the last, partial wave are cut into 2 or 4
+// column slices (>= 64 columns) when all slices still fit one wave.  WD_TAIL_SPLIT=0 keeps the plain schedule.
+int g_tail_split = getenv("WD_TAIL_SPLIT") ? atoi(getenv("WD_TAIL_SPLIT")) : 1;
+void strip_tail_split(wd::Conv2CtaStripArgs& p, int pairs, int BN) {
+    p.full_tiles = (p.num_tiles / pairs) * pairs;
+    const int tail = p.num_tiles - p.full_tiles;
+    p.split = 1;
+    if (g_tail_split && tail > 0 && !p.w_resident && p.full_tiles > 0) {
+        if (BN / 4 >= 64 && tail * 4 <= pairs) p.split = 4;
+        else if (BN / 2 >= 64 && tail * 2 <= pairs) p.split = 2;
+    }
+    p.tail_sub = tail * p.split;
+}
+
 // CTA-pair strip kernel: 3x3 stride 1, W streamed per tap, tile_n 128 or 256.
 template <int BN>
 int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
@@ -1025,6 +1039,7 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     const int total = p.off_bar + 2048 + 1024;
     int pairs = std::min(p.num_tiles, sm_count / 2);
     pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);
+    strip_tail_split(p, pairs, BN);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(288);
@@ -1076,6 +1091,7 @@ int launch_2cta_strip7(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, 
     const int total = p.off_bar + 2048 + 1024;
     int pairs = std::min(p.num_tiles, sm_count / 2);
     pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);
+    strip_tail_split(p, pairs, BN);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(288);
