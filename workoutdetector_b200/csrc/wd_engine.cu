@@ -936,7 +936,8 @@ bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
     if (a.residual != nullptr)  // conv3 of layers 3-4 (K >= 256): pair kernel with the in-place residual epilogue
         return g_2cta >= 4 && c.a_mode == wd::A_TMA && a.kblocks >= 4 && a.fold == 0;
     if (c.a_mode == wd::A_TMA) return a.kblocks >= 4 && (a.fold == 0 || a.fold % 64 == 0);
-    return g_2cta >= 3 && c.a_mode == wd::A_TAP && a.kblocks >= 8;   // stride-2 / 7x7 convolutions of layers 3-4
+    static const int tap_min_kb = getenv("WD_2CTA_TAP_MIN_KB") ? atoi(getenv("WD_2CTA_TAP_MIN_KB")) : 6;   // 6: layer2.0.conv3 (K = 128 + 256) too, 195 -> 172 us
+    return g_2cta >= 3 && c.a_mode == wd::A_TAP && a.kblocks >= tap_min_kb;   // stride-2 / 7x7 convolutions of layers 3-4
 }
 
 template <int BN, bool TAP, bool RES>
