@@ -377,10 +377,26 @@ def run_clips(args, rank, local_rank, world, dev, dist):
         dt = time.perf_counter() - t0
         d2h = int(lg.numel() * 4 + pb.numel() * 4 + st.numel() * 4)
         api = "wd_infer_u8_host_async x steps + wd_infer_host_sync (up to 3 batches in flight)"
+    # raw H2D rate with every rank copying at once (the limiter of the host-buffer paths at N = 8 is the host's memory
+    # bandwidth shared by eight PCIe links, not a collective): 5 copies of one pinned input set, barrier first
+    probe_dst = torch.empty_like(dev_sets[0])
+    probe_dst.copy_(host_sets[0], non_blocking=True)
+    sync_all()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(5):
+        probe_dst.copy_(host_sets[0], non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize(dev)
+    (probe_ms,) = max_over_ranks(p0.elapsed_time(p1))
+    del probe_dst
     dt, dt_sync = max_over_ranks(dt, dt_sync)
     e2e = dict(value=world * B * args.steps / dt, unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                steps=args.steps, api=api, blocking_call_value=world * B * args.steps / dt_sync,
-               h2d_gbs_per_gpu=h2d * args.steps / dt / 1e9, host_cpus_bound=ncpu)
+               h2d_gbs_per_gpu=h2d * args.steps / dt / 1e9, host_cpus_bound=ncpu,
+               h2d_probe_gbs_per_gpu=5 * h2d / (probe_ms * 1e-3) / 1e9,
+               h2d_note="h2d_gbs_per_gpu = bytes the timed e2e loop consumed per second; h2d_probe_gbs_per_gpu = "
+                        "cudaMemcpyAsync from pinned memory alone, all ranks copying at once (slowest rank)")
 
     frames = eng.preprocess_tdn_u8(dev_sets[0]) if tdn else eng.preprocess_u8(dev_sets[0])
     roofline = roofline_of(value / world, args.arch, clocks, eng, frames, B, ms / args.steps)

@@ -177,7 +177,8 @@ int wd_engine_num_ops(const wd_engine* e);
  *              a_mode (0 gather, 1 stem, 2 tma, 3 strip, -1 n/a), tile_n;   macs_per_clip = multiply-accumulates per clip */
 int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int32_t* info, double* macs_per_clip);
 /* After op `idx` runs in the next forwards, its output is converted to fp32 NCHW frames [n_clips*8, C, H, W]
- * at dst (device).  idx < 0 disables.  The head op (logits) cannot be tapped. */
+ * at dst (device).  idx < 0 disables.  The head op (logits) cannot be tapped.  idx + 65536 taps the SECOND output of a
+ * fused conv3 + next-conv1 op (that conv1's activation, [n_clips*8, its Cout, H, W]). */
 int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t capacity_elems);
 /* key: "use_tma_a" (0/1), "tile_n_max" (64/128/256), "persistent" (conv kernel generation: 0 one tile per CTA, 1 v2,
  * 2 v3, 3 v4 = default), "use_strip" (0/1: row-strip A operand for 3x3 stride-1 convolutions, v3/v4),

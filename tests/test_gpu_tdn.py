@@ -163,8 +163,11 @@ def test_tdn_bf16_ops_vs_bf16_emulation(tdn_engines, tdn_ref, tdn_gold, tdn_sd):
     for i, o in enumerate(ops):
         if o["kind"] != "mse":
             continue
-        assert ops[i - 1]["name"] == o["name"].replace(".mse", ".conv1")
-        xin = e.set_tap(i - 1, 2)
+        if ops[i - 1]["name"] == o["name"].replace(".mse", ".conv1"):
+            xin = e.set_tap(i - 1, 2)
+        else:   # this block's conv1 ran inside the previous block's conv3 kernel (conv_fuse3_kernel): tap its second output
+            assert ops[i - 1]["name"].endswith(".conv3") and o["name"].startswith(("layer2.", "layer3.0"))
+            xin = e.set_tap(i - 1, 2, second_cout=o["cout"])
         e.forward(clips)
         torch.cuda.synchronize()
         xin = xin.cpu().clone()

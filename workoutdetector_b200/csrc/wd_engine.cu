@@ -503,7 +503,7 @@ int build_plan_tdn(wd_engine* e) {
     int pre_c1 = -1, pre_buf = -1;
     auto bottleneck = [&](const std::string& pre, const std::string& nm, int inplanes, int width, int stride, int H,
                           bool mse, bool has_ds, int cur, int held, const std::string& next_pre,
-                          const std::string& next_nm) -> int {
+                          const std::string& next_nm, int next_width) -> int {
         int fr[3], nf = 0;
         for (int i = 0; i < kScratch && nf < 3; ++i)
             if (i != cur && i != held && i != pre_buf) fr[nf++] = i;
@@ -577,6 +577,19 @@ int build_plan_tdn(wd_engine* e) {
             o3.out2_buf = spare;
             o3.macs_per_clip += 8.0 * Ho * Ho * (double)width * outp;
         }
+        // Layer 2, blocks with an identity residual: conv3 + the next block's conv1 (512 -> 128, or layer3.0.conv1
+        // 512 -> 256) in conv_fuse3_kernel, as in the TSM plan but without TemporalShift (TDN shifts after the
+        // motion-excitation gate, tdn.py:366-376)
+        if (e->fuse3 && bf && !next_pre.empty() && outp == 512 && width == 128 && !has_ds && e->tile_n_max == 256 &&
+            e->use_tma_a && e->persistent >= 3) {
+            pre_c1 = add_conv(next_nm + ".conv1", next_pre + ".conv1", next_pre + ".bn1", outp, next_width, 1, 1, Ho, 1, true);
+            e->convs[pre_c1].fused_next = true;
+            pre_buf = spare;
+            Op& o3 = e->ops.back();
+            o3.conv2 = pre_c1;
+            o3.out2_buf = spare;
+            o3.macs_per_clip += 8.0 * Ho * Ho * (double)next_width * outp;
+        }
         return other;
     };
     auto layer = [&](const std::string& prefix, const std::string& name, int L, int H, bool mse, int cur, int held,
@@ -584,11 +597,14 @@ int build_plan_tdn(wd_engine* e) {
         int inplanes = L == 0 ? 64 : planes[L - 1] * 4;
         for (int b = 0; b < blocks[L]; ++b) {
             const int stride = (L > 0 && b == 0) ? 2 : 1;
-            const bool nxt = L == 0 && b + 1 < blocks[L];
+            const bool nxt = (L == 0 || (L == 1 && b > 0)) && b + 1 < blocks[L];
+            const bool nxt_layer = L == 1 && b + 1 == blocks[L];   // layer3.0.conv1 still runs at 28 x 28
             cur = bottleneck("base_model." + prefix + "." + std::to_string(b), name + "." + std::to_string(b), inplanes,
                              planes[L], stride, H, mse, b == 0, cur, held,
-                             nxt ? "base_model." + prefix + "." + std::to_string(b + 1) : std::string(),
-                             nxt ? name + "." + std::to_string(b + 1) : std::string());
+                             nxt ? "base_model." + prefix + "." + std::to_string(b + 1)
+                                 : (nxt_layer ? std::string("base_model.layer3_bak.0") : std::string()),
+                             nxt ? name + "." + std::to_string(b + 1) : (nxt_layer ? std::string("layer3.0") : std::string()),
+                             nxt_layer ? planes[L + 1] : planes[L]);
             if (stride == 2) H /= 2;
             inplanes = planes[L] * 4;
         }
@@ -1734,6 +1750,16 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
             WD_CUDA(cudaGetLastError());
             ++e->launches;
         }
+        if ((int)oi == e->tap_idx - 65536 && e->tap_dst && o.conv2 >= 0) {   // second output of a fused conv3 + conv1 op
+            const int C2 = e->convs[o.conv2].Cout;
+            const size_t total = (size_t)n_clips * 8 * C2 * o.H * o.W;
+            if ((int64_t)total > e->tap_cap)
+                return fail(WD_ERR_INVALID, "tap buffer too small: need %zu elements, have %lld", total,
+                            (long long)e->tap_cap);
+            wd::untile_to_nchw_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(e->buf[o.out2_buf]), e->tap_dst, n_clips, o.H, o.W, C2);
+            WD_CUDA(cudaGetLastError());
+        }
         if ((int)oi == e->tap_idx && e->tap_dst && o.kind != OP_HEAD) {
             const size_t total = (size_t)n_clips * 8 * o.C * o.H * o.W;
             if ((int64_t)total > e->tap_cap)
@@ -1869,7 +1895,7 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->fuse2_requested = getenv("WD_FUSE2") ? atoi(getenv("WD_FUSE2")) : 2;  // 1: inside layer 1, 2: + layer2.0.conv1
     e->fuse2 = e->fuse2_requested;
     e->fuse3_requested = getenv("WD_FUSE3") ? atoi(getenv("WD_FUSE3")) : 1;
-    e->fuse3 = d->arch == WD_ARCH_TSM_R50 ? e->fuse3_requested : 0;
+    e->fuse3 = e->fuse3_requested;   // TSM layer 2 (shift fold 64) and TDN layer 2 (no shift in conv1)
     e->fuse3_safe = getenv("WD_FUSE3_SAFE") ? atoi(getenv("WD_FUSE3_SAFE")) : 1;
     int r = d->arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e);
     if (r != WD_OK) {
@@ -1977,8 +2003,7 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
     {
         const int want_fuse = (e->use_tma_a && e->persistent >= 3) ? e->fuse_ds_requested : 0;
         const int want_f2 = (want_fuse >= 1 && e->tile_n_max == 256) ? e->fuse2_requested : 0;
-        const int want_f3 = (e->desc.arch == WD_ARCH_TSM_R50 && e->use_tma_a && e->persistent >= 3 && e->tile_n_max == 256)
-                                ? e->fuse3_requested : 0;
+        const int want_f3 = (e->use_tma_a && e->persistent >= 3 && e->tile_n_max == 256) ? e->fuse3_requested : 0;
         if (want_fuse != e->fuse_ds || want_f2 != e->fuse2 || want_f3 != e->fuse3) {
             for (auto& c : e->convs) {
                 if (c.w_packed) cudaFree(c.w_packed);
@@ -2418,8 +2443,15 @@ static int infer_u8_host_impl(wd_engine* e, const uint8_t* host, int n_clips, in
     cudaStream_t cp = e->hstream[1];
     int done = 0;
     bool first = true;
+    int chunk_no = 0;
     while (done < n_clips) {
-        const int nc = std::min(first ? first_chunk : chunk, n_clips - done);
+        int nc = std::min(first ? first_chunk : chunk, n_clips - done);
+        // Synchronous call, second chunk: about a third of what is left (at least 8 clips).  Its copy then hides behind
+        // the first chunk's convolutions and the last chunk's copy behind its own — also when eight ranks share the
+        // host's memory bandwidth (8 x B200: 32 GB/s per GPU instead of 55; an (8, 56) schedule exposed 2 ms there).
+        if (!async && chunk_no == 1 && env_chunk <= 0 && n_clips - done > 16)
+            nc = std::min(nc, std::max(8, (int)((n_clips - done) * 0.36f + 0.5f)));
+        ++chunk_no;
         first = false;
         const int slot = (int)(e->h_idx % kHostSlots);
         // wait until the compute that last used this slot has finished before overwriting its staging buffer
@@ -2501,7 +2533,13 @@ int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int
 
 int wd_engine_set_tap(wd_engine* e, int idx, float* dst, int64_t cap) {
     if (!e) return fail(WD_ERR_INVALID, "engine is NULL");
-    if (idx >= (int)e->ops.size()) return fail(WD_ERR_INVALID, "tap index out of range");
+    if (idx >= 65536) {   // second output (the next block's conv1) of a fused conv3 + conv1 op
+        const int base = idx - 65536;
+        if (base >= (int)e->ops.size() || e->ops[base].conv2 < 0)
+            return fail(WD_ERR_INVALID, "op %d has no second output to tap", base);
+    } else if (idx >= (int)e->ops.size()) {
+        return fail(WD_ERR_INVALID, "tap index out of range");
+    }
     e->tap_idx = idx;
     e->tap_dst = dst;
     e->tap_cap = cap;

@@ -103,15 +103,17 @@ class Engine:
                             a_mode=A_MODES[info[8]], tile_n=info[9], macs_per_clip=macs.value))
         return out
 
-    def set_tap(self, idx: int, n_clips: int = 1) -> Optional[torch.Tensor]:
-        """Capture op idx's output as fp32 NCHW frames on the next forwards; idx < 0 disables."""
+    def set_tap(self, idx: int, n_clips: int = 1, second_cout: int = 0) -> Optional[torch.Tensor]:
+        """Capture op idx's output as fp32 NCHW frames on the next forwards; idx < 0 disables.  ``second_cout`` > 0: the
+        op is a fused conv3 + next-conv1 launch and the SECOND output (that conv1's activation, ``second_cout`` channels)
+        is captured instead."""
         if idx < 0:
             check(self.lib.wd_engine_set_tap(self.h, -1, None, 0))
             self._tap = None
             return None
         o = self.ops()[idx]
-        t = torch.empty((n_clips * 8, o["cout"], o["hout"], o["wout"]), dtype=torch.float32, device=self.device)
-        check(self.lib.wd_engine_set_tap(self.h, idx, _ptr(t), t.numel()))
+        t = torch.empty((n_clips * 8, second_cout or o["cout"], o["hout"], o["wout"]), dtype=torch.float32, device=self.device)
+        check(self.lib.wd_engine_set_tap(self.h, idx + (65536 if second_cout else 0), _ptr(t), t.numel()))
         self._tap = t
         return t
 
