@@ -221,6 +221,9 @@ CONV_CASES = [
     (2, 56, 128, 128, 3, 2, 0, 1, 0, "tap", 128),         # 56 -> 28: two 14-pixel segments per row
     (8, 7, 512, 512, 3, 1, 0, 1, 0, "tap", 256),          # 7x7 conv2 on the pair strip kernel (two image rows per CTA tile), 56 rows = 14 pair tiles x 2
     (5, 7, 128, 256, 3, 1, 0, 0, 0, "tap", 256),          # ... odd row count (35), one n-tile, no ReLU
+    (3, 28, 256, 256, 3, 2, 0, 1, 0, "tap", 256),         # stride 2 on the pair strip kernel: 28 -> 14, one 29-pixel row box per tap row, stride in the MMA descriptor
+    (5, 14, 512, 512, 3, 2, 0, 0, 0, "tap", 256),         # ... 14 -> 7: two 15-pixel boxes per tap row, odd row count, no ReLU
+    (64, 14, 512, 512, 3, 2, 0, 1, 0, "tap", 256),        # ... layer4.0.conv2 at batch 64 (224 pair tiles: tail split)
     (64, 7, 512, 512, 3, 1, 0, 1, 0, "tap", 256),         # ... 224 pair tiles on 74 pairs: the two left-over tiles run as eight 64-column slices
     (33, 14, 256, 256, 3, 1, 0, 1, 0, "strip", 256),      # pair strip kernel, 231 tiles: 9 left-over tiles as 36 slices
     (19, 28, 128, 128, 3, 1, 0, 0, 0, "strip", 128),      # tile_n 128 on the pair strip kernel path (forced by WD_STRIP2=0 only), tail of 2-column-slice splits

@@ -444,7 +444,9 @@ struct Conv2CtaStripArgs {
     int tiles_w;       // W / 14
     int w_stages;      // W ring depth
     int w_resident;    // w_stages == 9 * cin_blocks: every tap's W half is loaded once and stays (layer 1, Cin = 64)
-    int num_rows7;     // W7: clips * 7 (clip, h) rows; a strip is two of them
+    int num_rows7;     // two-row tiles (7-pixel output rows): clips * 7 (clip, h) rows; a strip is two of them
+    int s2_prefetch;   // MODE 2: L2 prefetch of the next channel block's row box
+    int s2_two;        // MODE 2 (stride 2): 1 = 7-pixel output rows, two per tile; 0 = one 14-pixel strip per tile
     // Tail split: the tiles of the last, partial wave (num_tiles % pairs of them) are cut into `split` column slices of
     // BN / split columns each, so that up to `split` times as many pairs share that wave (224 tiles on 74 pairs are
     // 3.03 waves: the two left-over tiles become eight 64-column ones).  full_tiles = tiles in complete waves (a
@@ -461,15 +463,26 @@ struct Conv2CtaStripArgs {
 // are contiguous in the [rows, C] output, so warps 0 / 3 store 32 rows, warps 1 / 2 store 24 (`omap16` is then the
 // 24-row map; warp 2 stores from row 8 of its slab).  One box per (tap row, sub-row, channel block) instead of tap
 // mode's one box per (tap, sub-row, channel block): a third of the A fill traffic through shared memory.
-template <int BN, bool W7 = false>
+//
+// MODE 2: 3x3 STRIDE-2 convolutions (layer3.0 / layer4.0 conv2) without tap boxes.  The input row 2h - 1 + dh of a
+// 14-pixel output strip is ONE contiguous box of 29 pixels (x = 28 ws - 1 ...; two 15-pixel boxes, 18 slots apart, for
+// two 7-pixel output rows) and the stride lives in the MMA descriptor: one pixel is one 1024-byte swizzle atom in the
+// T-inner layout, so a stride-byte-offset of 2048 reads every second pixel (the trick of conv_strip2d_kernel); tap
+// (dh, dw) starts at slot dw of tap-row buffer dh.  A tap-row buffer is 33 KiB, so there is no second A stage: the three
+// tap-row buffers are their own ring (producer warp r owns buffer r, barrier pair per buffer) — the reload of row dh
+// for the next channel block runs under the six taps of the other two rows.
+template <int BN, int MODE = 0>
 __global__ void __launch_bounds__(288, 1)
 conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
                        const Conv2CtaStripArgs a) {
     constexpr int kWHalf = (BN / 2) * kTileK * 2;  // this CTA's half of one tap's W tile
     constexpr int kAStages = 2;
-    constexpr int kRowBuf = W7 ? 18 * 1024 : 16384;   // one tap row of the A stage
+    constexpr bool W7 = MODE == 1;
+    constexpr bool S2 = MODE == 2;
+    constexpr int kRowBuf = W7 ? 18 * 1024 : (S2 ? 33 * 1024 : 16384);   // one tap row of the A stage
     constexpr int kAStage = 3 * kRowBuf;
+    constexpr uint32_t kDescHiS2 = (2048u >> 4) | (1u << 14) | (2u << 29);   // SWIZZLE_128B K-major, SBO = 2048
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
@@ -477,7 +490,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
     uint8_t* sOut = smem + a.off_out;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
     uint64_t* a_full = bars;               // [2]  (leader's)
-    uint64_t* a_empty = bars + 2;          // [2]
+    uint64_t* a_empty = bars + (S2 ? 4 : 2);   // [2]  (S2: a_full[3] = bars 0..2, a_empty[3] = bars 4..6, one pair per tap row)
     uint64_t* w_full = bars + 8;           // [16]  (leader's)
     uint64_t* w_empty = bars + 24;         // [16]
     uint64_t* tmem_full_bar = bars + 40;   // [2]
@@ -500,8 +513,8 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
             tma_prefetch_desc(&amap);
             tma_prefetch_desc(&omap);
             tma_prefetch_desc(&omap16);
-            for (int s = 0; s < kAStages; ++s) {
-                mbar_init(&a_full[s], 6);
+            for (int s = 0; s < (S2 ? 3 : kAStages); ++s) {
+                mbar_init(&a_full[s], S2 ? 2 : 6);
                 mbar_init(&a_empty[s], 1);
             }
             for (int s = 0; s < 16; ++s) {
@@ -562,9 +575,10 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
             const int chunks = nc >> 6;
             const float* bias_src = (n0 == cta_n0) ? sBias : a.bias + n0;   // tail slices of another n-tile: from global
             // W7: sub-row A (warps 0, 1) is live when 2 * strip < rows, sub-row B (warps 2, 3) when 2 * strip + 1 < rows
-            const bool live = W7 ? (2 * strip + (warp >> 1) < a.num_rows7) : (strip < a.num_strips);
+            const bool two = W7 || (S2 && a.s2_two);
+            const bool live = two ? (2 * strip + (warp >> 1) < a.num_rows7) : (strip < a.num_strips);
             // strips are consecutive 112-row groups of the output
-            const int mrow = strip * kStripRows + (W7 ? (warp == 0 ? 0 : warp == 1 ? 32 : warp == 2 ? 56 : 80) : warp * 32);
+            const int mrow = strip * kStripRows + (two ? (warp == 0 ? 0 : warp == 1 ? 32 : warp == 2 ? 56 : 80) : warp * 32);
             const int acc = tile_iter & 1;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN;
             const uint32_t leader_empty = mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0);
@@ -612,7 +626,7 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                 if (elect_one()) {
                     if (live) {
                         const uint8_t* src = my_out + (chunk_idx & 1) * kEpiSlab;
-                        if (W7) {
+                        if (two) {
                             if (warp == 1) tma_store_2d(&omap16, src, n0 + c * 64, mrow);               // slots 4..6
                             else if (warp == 2) tma_store_2d(&omap16, src + 1024, n0 + c * 64, mrow);   // slots 9..11
                             else tma_store_2d(&omap, src, n0 + c * 64, mrow);
@@ -665,9 +679,11 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int cb = 0; cb < a.cin_blocks; ++cb, ++ita) {
-                    const int aslot = ita % kAStages;
-                    mbar_wait(&a_full[aslot], (ita / kAStages) & 1);
-                    tc_fence_after_sync();
+                    const int aslot = S2 ? 0 : ita % kAStages;
+                    if (!S2) {
+                        mbar_wait(&a_full[aslot], (ita / kAStages) & 1);
+                        tc_fence_after_sync();
+                    }
                     const uint32_t a_lo = sA_lo + ((uint32_t)(aslot * kAStage) >> 4);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap, ++itw) {
@@ -676,8 +692,12 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                             mbar_wait(&w_full[wslot], (itw / a.w_stages) & 1);
                             tc_fence_after_sync();
                         }
-                        const uint64_t adesc =
-                            umma_desc_from_lo(a_lo + (uint32_t)((tap / 3) * (kRowBuf >> 4) + (tap % 3) * (1024 >> 4)));
+                        if (S2 && tap % 3 == 0) {   // tap row dh = tap / 3 of this channel block has landed
+                            mbar_wait(&a_full[tap / 3], ita & 1);
+                            tc_fence_after_sync();
+                        }
+                        const uint32_t a_tap_lo = a_lo + (uint32_t)((tap / 3) * (kRowBuf >> 4) + (tap % 3) * (1024 >> 4));
+                        const uint64_t adesc = S2 ? ((static_cast<uint64_t>(kDescHiS2) << 32) | a_tap_lo) : umma_desc_from_lo(a_tap_lo);
                         const uint64_t bdesc = umma_desc_from_lo(sW_lo + ((uint32_t)(wslot * kWHalf) >> 4));
                         const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
                         if (elect_one()) {
@@ -686,8 +706,9 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
                             for (int k = 1; k < kTileK / 16; ++k)
                                 umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                             if (!a.w_resident) umma_commit_2cta(&w_empty[wslot]);
+                            if (S2 && tap % 3 == 2) umma_commit_2cta(&a_empty[tap / 3]);
                             if (tap == 8) {
-                                umma_commit_2cta(&a_empty[aslot]);
+                                if (!S2) umma_commit_2cta(&a_empty[aslot]);
                                 if (cb == a.cin_blocks - 1) umma_commit_2cta(&tmem_full_bar[acc]);
                             }
                         }
@@ -703,19 +724,36 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         int tile, n0, nc;
         for (int w = pair; work_of(w, tile, n0, nc); w += npairs) {
             const int strip = strip_of(tile);
-            const int ws = W7 ? 0 : strip % a.tiles_w;
-            const int q = W7 ? 2 * strip : strip / a.tiles_w;
+            const bool two = W7 || (S2 && a.s2_two);
+            const int ws = two ? 0 : strip % a.tiles_w;
+            const int q = two ? 2 * strip : strip / a.tiles_w;
             const int h = q % a.Hout;
             const int n = q / a.Hout;  // past-the-end strips have n >= clips: the whole box is out of bounds -> zeros
             const int hb = (q + 1) % a.Hout, nb = (q + 1) / a.Hout;   // W7: sub-row B
             for (int cb = 0; cb < a.cin_blocks; ++cb, ++it) {
-                const int slot = it % kAStages;
-                mbar_wait(&a_empty[slot], ((it / kAStages) & 1) ^ 1);
+                const int slot = S2 ? prow : (int)(it % kAStages);
+                if (S2) mbar_wait(&a_empty[slot], (it & 1) ^ 1);
+                else mbar_wait(&a_empty[slot], ((it / kAStages) & 1) ^ 1);
                 const uint32_t leader_full = mapa_shared(smem_u32(&a_full[slot]), 0);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx_cluster(leader_full, kRowBuf);
-                    uint8_t* dst = sA + slot * kAStage + prow * kRowBuf;
-                    if (W7) {
+                    mbar_arrive_expect_tx_cluster(leader_full, S2 ? (two ? 2 * 15 * 1024 : 29 * 1024) : kRowBuf);
+                    uint8_t* dst = sA + (S2 ? 0 : slot * kAStage) + prow * kRowBuf;
+                    if (S2) {
+                        // amap here is the INPUT view {C, 8, Win, Hin, clips}: box of 15 (two-row tiles) or 29 pixels
+                        // the buffer is single: pull the next channel block of this row into L2 while this one is consumed
+                        const bool pf = a.s2_prefetch && cb + 1 < a.cin_blocks;
+                        if (two) {
+                            tma_load_5d_2cta(&amap, leader_full, dst, cb * kTileK, 0, -1, 2 * h - 1 + prow, n);
+                            tma_load_5d_2cta(&amap, leader_full, dst + 18 * 1024, cb * kTileK, 0, -1, 2 * hb - 1 + prow, nb);
+                            if (pf) {
+                                tma_prefetch_l2_5d(&amap, (cb + 1) * kTileK, 0, -1, 2 * h - 1 + prow, n);
+                                tma_prefetch_l2_5d(&amap, (cb + 1) * kTileK, 0, -1, 2 * hb - 1 + prow, nb);
+                            }
+                        } else {
+                            tma_load_5d_2cta(&amap, leader_full, dst, cb * kTileK, 0, 2 * ws * kStripPixels - 1, 2 * h - 1 + prow, n);
+                            if (pf) tma_prefetch_l2_5d(&amap, (cb + 1) * kTileK, 0, 2 * ws * kStripPixels - 1, 2 * h - 1 + prow, n);
+                        }
+                    } else if (W7) {
                         tma_load_5d_2cta(&amap, leader_full, dst, cb * kTileK, 0, -1, h - 1 + prow, n);
                         tma_load_5d_2cta(&amap, leader_full, dst + 9 * 1024, cb * kTileK, 0, -1, hb - 1 + prow, nb);
                     } else {

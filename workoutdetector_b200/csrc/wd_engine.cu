@@ -1075,17 +1075,20 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
     return WD_OK;
 }
 
-// 3x3 stride-1 convolutions on 7 x 7 images (layer4.1 / layer4.2 conv2): the pair strip kernel with two image rows per
-// CTA tile (conv_2cta_strip_kernel<256, true>) instead of tap boxes.  WD_STRIP7=0 keeps the tap-mode pair kernel.
-int g_strip7 = getenv("WD_STRIP7") ? atoi(getenv("WD_STRIP7")) : 1;
-int launch_2cta_strip7(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+// 3x3 stride-1 convolutions on 7 x 7 images (layer4.1 / layer4.2 conv2: conv_2cta_strip_kernel<256, 1>, two image rows per
+// CTA tile) and the stride-2 3x3 convolutions of layers 3-4 (conv_2cta_strip_kernel<256, 2>) on the pair strip kernel
+// instead of tap boxes.  WD_STRIP7=0 keeps the tap-mode pair kernel for all of them, 1 = stride 1 only, 2 = both.
+int g_strip7 = getenv("WD_STRIP7") ? atoi(getenv("WD_STRIP7")) : 2;
+template <int MODE>   // 1: 7 x 7 images, stride 1 (two image rows per tile); 2: stride 2 (row boxes + stride in the MMA descriptor)
+int launch_2cta_strip_mode(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     constexpr int BN = 256;
     static bool configured = false;
-    auto kfn = wd::conv_2cta_strip_kernel<BN, true>;
+    auto kfn = wd::conv_2cta_strip_kernel<BN, MODE>;
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
+    const bool two = a.Wout == 7;                 // two 7-pixel output rows per CTA tile
     wd::Conv2CtaStripArgs p{};
     p.bias = a.bias;
     p.Hout = a.Hout;
@@ -1093,16 +1096,19 @@ int launch_2cta_strip7(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, 
     p.cin_blocks = a.cin_blocks;
     p.relu = a.relu;
     p.n_tiles = c.Cout / BN;
-    p.tiles_w = 1;
-    p.num_rows7 = a.M / 56;                       // (clip, h) rows of 7 pixels x 8 segments
-    p.num_strips = (p.num_rows7 + 1) / 2;
+    p.tiles_w = two ? 1 : a.Wout / wd::kStripPixels;
+    p.s2_two = two ? 1 : 0;
+    static const int s2_prefetch = getenv("WD_S2_PREFETCH") ? atoi(getenv("WD_S2_PREFETCH")) : 0;   // measured neutral
+    p.s2_prefetch = s2_prefetch;
+    p.num_rows7 = a.M / 56;                       // (clip, h) rows of 7 pixels x 8 segments (two-row tiles)
+    p.num_strips = two ? (p.num_rows7 + 1) / 2 : a.M / wd::kStripRows;
     p.num_tiles = ((p.num_strips + 1) / 2) * p.n_tiles;
     const int whalf = (BN / 2) * 128;
-    const int a_stage = 3 * 18 * 1024;
-    const int fixed = 2 * a_stage + 8 * wd::kEpiSlab + 2048 + 1024;
+    const int a_bytes = MODE == 2 ? 3 * 33 * 1024 : 2 * 3 * 18 * 1024;
+    const int fixed = a_bytes + 8 * wd::kEpiSlab + 2048 + 1024;
     p.w_stages = std::min(8, (232448 - fixed) / whalf);
     p.w_resident = 0;
-    p.off_w = 2 * a_stage;
+    p.off_w = a_bytes;
     p.off_out = p.off_w + p.w_stages * whalf;
     p.off_bar = p.off_out + 8 * wd::kEpiSlab;
     const int total = p.off_bar + 2048 + 1024;
@@ -1123,7 +1129,7 @@ int launch_2cta_strip7(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, 
     attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap9, c.omap, c.omap24, p));
+    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap9, c.omap, two ? c.omap24 : c.omap16, p));
     return WD_OK;
 }
 
@@ -1212,7 +1218,8 @@ int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
     if (g_strip2 && c.a_mode == wd::A_STRIP && c.tile_n == 64 && c.Cin == 64 && c.Cout == 64 && a.residual == nullptr &&
         a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
         return launch_strip2(c, a, sm_count, st);
-    if (g_strip7 && g_2cta >= 3 && c.has_strip7 && a.residual == nullptr && a.fold == 0) return launch_2cta_strip7(c, a, sm_count, st);
+    if (g_strip7 && g_2cta >= 3 && c.has_strip7 && a.residual == nullptr && a.fold == 0)
+        return c.stride == 2 ? launch_2cta_strip_mode<2>(c, a, sm_count, st) : launch_2cta_strip_mode<1>(c, a, sm_count, st);
     if (eligible_2cta(c, a)) return launch_2cta(c, a, sm_count, st);
     if (g_2cta >= 5 && c.a_mode == wd::A_STRIP && a.residual == nullptr && c.tile_n == 64)
         return launch_2cta_strip<64>(c, a, sm_count, st);  // narrow tiles on a CTA pair: 256 x 64 per instruction
@@ -1402,11 +1409,11 @@ int make_amap5(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t
 }
 
 // 7 x 7 strip mode: the same 5-D view with a 9-pixel box (x = -1 .. 7 of one image row).
-int make_amap9(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t clips) {
+int make_amap9(CUtensorMap* map, const void* base, int Cin, int W, int H, size_t clips, int box_w = 9) {
     const uint64_t dims[5] = {(uint64_t)Cin, 8, (uint64_t)W, (uint64_t)H, (uint64_t)clips};
     const uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16, (uint64_t)W * Cin * 16,
                                  (uint64_t)H * W * Cin * 16};
-    const uint32_t box[5] = {64, 8, 9, 1, 1};
+    const uint32_t box[5] = {64, 8, (uint32_t)box_w, 1, 1};
     return make_tmap_bf16(map, base, 5, dims, strides, box);
 }
 
@@ -2124,6 +2131,14 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                     WD_TRY(make_omap(&c.omap24, e->buf[o.out_buf], c.Cout, rows, 24));
                     c.has_strip7 = true;
                 }
+                if (g_strip7 >= 2 && c.k == 3 && c.stride == 2 && (c.Wout == 7 || c.Wout == wd::kStripPixels) &&
+                    c.Hout == c.Wout && c.Win == 2 * c.Wout && c.tile_n == 256 && c.Cout % 256 == 0 && c.Cin % 64 == 0 &&
+                    c.fold == 0 && o.res_buf < 0 && c.kb_split == 0 && !c.s2d) {   // layer3.0 / layer4.0 conv2
+                    WD_TRY(make_amap9(&c.amap9, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips,
+                                      c.Wout == 7 ? 15 : 29));
+                    WD_TRY(make_omap(&c.omap24, e->buf[o.out_buf], c.Cout, rows, 24));
+                    c.has_strip7 = true;
+                }
                 if (o.in2_buf >= 0) {  // fused stride-2 downsample: the block input at twice the resolution
                     const ConvLayer& d = e->convs[c.fuse_ds];
                     WD_TRY(make_amap_tap(&c.amap32, e->buf[o.in2_buf], d.Cin, d.Win, d.Hin, (size_t)e->desc.max_clips,
@@ -2583,6 +2598,13 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
             if (rc == WD_OK && ksize == 3 && stride == 1 && c.Wout == 7 && c.Hout == 7 && c.tile_n == 256 && Cout % 256 == 0 &&
                 Cin % 64 == 0 && fold == 0 && !residual) {
                 rc = make_amap9(&c.amap9, x, Cin, Win, Hin, (size_t)clips);
+                if (rc == WD_OK) rc = make_omap(&c.omap24, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 24);
+                c.has_strip7 = rc == WD_OK;
+            }
+            if (rc == WD_OK && g_strip7 >= 2 && ksize == 3 && stride == 2 && (c.Wout == 7 || c.Wout == wd::kStripPixels) &&
+                c.Hout == c.Wout && Win == 2 * c.Wout && c.tile_n == 256 && Cout % 256 == 0 && Cin % 64 == 0 && fold == 0 &&
+                !residual) {
+                rc = make_amap9(&c.amap9, x, Cin, Win, Hin, (size_t)clips, c.Wout == 7 ? 15 : 29);
                 if (rc == WD_OK) rc = make_omap(&c.omap24, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 24);
                 c.has_strip7 = rc == WD_OK;
             }
