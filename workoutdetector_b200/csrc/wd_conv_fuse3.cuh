@@ -37,7 +37,11 @@ struct Fuse3Args {
     int M;                // rows (clips * H * W * 8), a multiple of 128
     int num_tiles;        // M / 128
     int n_chunks;         // N1 / 128 (4)
-    int w_stages;         // ring depth (3)
+    int w_stages;         // ring depth
+    const uint8_t* res_base;   // residual [rows, N1] bf16 (nullable): the next tile's 128 rows are one contiguous span,
+    int res_tile_bytes;        // pulled into L2 with ONE bulk prefetch while this tile computes
+    int a_slots;          // 2: the next tile's A loads under this tile; 1: one slot (32 KiB more for the W ring), the
+                          // next tile is prefetched into L2 instead
     int shift;            // 1: the second convolution sees TemporalShift(y), fold 64
     int safe_order;       // 1: M1(g+2) is issued only after M2(g) has COMPLETED (y_free barrier) instead of relying on the
                           // in-order execution of tcgen05.mma for the write-after-read on chunk g's TMEM columns
@@ -57,7 +61,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
     constexpr int kStagesPerM2 = N2 / 128;   // ring stages one M2 consumes (one per k-block when N2 = 256)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sA = smem;                      // 2 slots x (2 k-blocks x 16 KiB)
+    uint8_t* sA = smem;                      // a_slots x (2 k-blocks x 16 KiB)
     uint8_t* sW = smem + a.off_w;
     uint8_t* sOut = smem + a.off_out;        // 8 warps x 3 slabs x 4 KiB: residual in, result out (in place)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
@@ -330,8 +334,8 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
         uint32_t itw = 0;   // ring stages consumed
         auto first = [&](uint32_t gg) {    // M1(gg): acc1[gg & 1] = A(tile) * W3(chunk)^T
             const uint32_t ti = gg / (uint32_t)n_chunks, j = gg % (uint32_t)n_chunks;
-            const uint32_t aslot = ti & 1u;
-            if (j == 0) mbar_wait(&a_full[aslot], (ti >> 1) & 1u);
+            const uint32_t aslot = a.a_slots == 2 ? (ti & 1u) : 0u;
+            if (j == 0) mbar_wait(&a_full[aslot], (a.a_slots == 2 ? (ti >> 1) : ti) & 1u);
             if (a.safe_order && gg >= 2) mbar_wait(&y_free[gg & 1u], ((gg - 2) >> 1) & 1u);
             const uint32_t slot = itw % (uint32_t)a.w_stages;
             mbar_wait(&w_full[slot], (itw / (uint32_t)a.w_stages) & 1u);
@@ -396,8 +400,17 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int px0 = (tile * kTileM) >> 3;
-            const uint32_t slot = ti & 1u;
-            mbar_wait(&a_empty[slot], ((ti >> 1) & 1u) ^ 1u);
+            if (a.res_base && tile + (int)gridDim.x < num_tiles && elect_one())
+                bulk_prefetch_l2(a.res_base + (size_t)(tile + (int)gridDim.x) * (size_t)a.res_tile_bytes, (uint32_t)a.res_tile_bytes);
+            __syncwarp();
+            const uint32_t slot = a.a_slots == 2 ? (ti & 1u) : 0u;
+            if (a.a_slots == 1 && tile + (int)gridDim.x < num_tiles && elect_one()) {   // next tile -> L2 while this one computes
+                const int pxn = ((tile + (int)gridDim.x) * kTileM) >> 3;
+                tma_prefetch_l2_3d(&amap, 0, 0, pxn);
+                tma_prefetch_l2_3d(&amap, kTileK, 0, pxn);
+            }
+            __syncwarp();
+            mbar_wait(&a_empty[slot], ((a.a_slots == 2 ? (ti >> 1) : ti) & 1u) ^ 1u);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&a_full[slot], 2 * kATileBytes);
                 tma_load_3d(&amap, &a_full[slot], sA + slot * 32768, 0, 0, px0);

@@ -1563,7 +1563,7 @@ int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool h
 
 // Layer 2: conv3 (+ identity residual) of a block + conv1 of the next block in one kernel (wd_conv_fuse3.cuh).
 template <int N2>
-int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int n_clips, cudaStream_t st) {
+int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, const void* res, int n_clips, cudaStream_t st) {
     static bool configured = false;
     auto kfn = wd::conv_fuse3_kernel<N2>;
     if (!configured) {
@@ -1579,9 +1579,17 @@ int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
     p.n_chunks = c3.Cout / wd::kF3Chunk;
     p.shift = c1n.fold == 64 ? 1 : 0;
     p.safe_order = e->fuse3_safe;
-    p.w_stages = 2;
-    // shared memory: 2 A slots (32 KiB each) | W ring | 8 warps x 3 in-place residual / output slabs | barriers
-    p.off_w = 2 * 32768;
+    // Two measured dead ends, kept as switches: WD_F3_RES_PREFETCH=1 (one 128 KiB bulk L2 prefetch of the next tile's
+    // residual per tile: 195 -> 232 us, the prefetch competes with the demand loads) and WD_F3_ASLOTS=1 (one A slot, three
+    // W stages: 185 -> 196 us for N2 = 128, 251 -> 248 us for N2 = 256: the W ring is not what starves the kernel).
+    static const int f3_res_pf = getenv("WD_F3_RES_PREFETCH") ? atoi(getenv("WD_F3_RES_PREFETCH")) : 0;
+    p.res_base = f3_res_pf ? static_cast<const uint8_t*>(res) : nullptr;
+    p.res_tile_bytes = wd::kTileM * c3.Cout * 2;
+    static const int f3_aslots = getenv("WD_F3_ASLOTS") ? atoi(getenv("WD_F3_ASLOTS")) : 2;
+    p.a_slots = f3_aslots == 1 ? 1 : 2;
+    p.w_stages = p.a_slots == 1 ? 3 : 2;
+    // shared memory: A slots (32 KiB each) | W ring | 8 warps x 3 in-place residual / output slabs | barriers
+    p.off_w = p.a_slots * 32768;
     p.off_out = p.off_w + p.w_stages * wd::kF3WStage;
     p.off_bar = p.off_out + 8 * 3 * wd::kEpiSlab;
     const size_t smem = (size_t)p.off_bar + 1024 + 1024;
@@ -1592,13 +1600,14 @@ int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
     return WD_OK;
 }
 
-int launch_fuse3(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool has_res, int n_clips, cudaStream_t st) {
+int launch_fuse3(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, const void* res, int n_clips, cudaStream_t st) {
+    const bool has_res = res != nullptr;
     if (!has_res || c3.tile_n != 256 || c3.Cout % 256 != 0 || c3.Cin != 128 || c3.kblocks != 2 || c3.kb_split != 0 ||
         c3.a_mode != wd::A_TMA || c1n.Cin != c3.Cout || (c1n.Cout != 128 && c1n.Cout != 256) || c1n.tile_n != c1n.Cout ||
         (c1n.fold != 64 && c1n.fold != 0) || c3.Cout != 512)
         return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused layer-2 conv3 + conv1 kernel", c3.name.c_str(),
                     c1n.name.c_str());
-    return c1n.Cout == 128 ? launch_fuse3_t<128>(e, c3, c1n, n_clips, st) : launch_fuse3_t<256>(e, c3, c1n, n_clips, st);
+    return c1n.Cout == 128 ? launch_fuse3_t<128>(e, c3, c1n, res, n_clips, st) : launch_fuse3_t<256>(e, c3, c1n, res, n_clips, st);
 }
 
 // Motion excitation + temporal Conv1d of one BottleneckShift: four launches (wd_tdn_kernels.cuh).
@@ -1684,7 +1693,7 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
                 WD_CUDA(cudaGetLastError());
             } else if (o.conv2 >= 0 && c.Cout == 512) {
-                WD_TRY(launch_fuse3(e, c, e->convs[o.conv2], res != nullptr, n_clips, st));
+                WD_TRY(launch_fuse3(e, c, e->convs[o.conv2], res, n_clips, st));
             } else if (o.conv2 >= 0) {
                 WD_TRY(launch_fuse2(e, c, e->convs[o.conv2], res != nullptr, n_clips, st));
             } else if (o.in_buf == kInDiff && c.a_mode == wd::A_TAP) {

@@ -201,6 +201,10 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c
                  : "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// contiguous span -> L2 (no shared-memory destination, no completion tracking); size a multiple of 16 bytes
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];"
                  :
