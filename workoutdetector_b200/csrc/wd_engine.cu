@@ -1623,6 +1623,8 @@ int launch_mse(const MseLayer& ml, const void* in, void* out, float* scratch, in
         configured = true;
     }
     const int C = ml.C, H = ml.H, W = ml.W;
+    if ((size_t)n_clips * H * W >= ((size_t)1 << 31))   // the kernels decode pixel indices with 32-bit divisions
+        return fail(WD_ERR_INVALID, "motion excitation: %d clips x %d x %d pixels exceed the 32-bit pixel index", n_clips, H, W);
     if (ml.r != R || C > 512) return fail(WD_ERR_INVALID, "motion excitation: unsupported width %d", C);
     const size_t P = (size_t)n_clips * H * W, rows = P * 8;
     const size_t P2 = (size_t)n_clips * (H / 2) * (W / 2);
@@ -1721,9 +1723,16 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
         } else if (o.kind == OP_BLEND) {  // x = alpha x + beta up(y); 0.5 / 0.5 for 8 segments (tdn.py:192-193)
             const size_t total = (size_t)n_clips * o.H * o.W * 8 * (o.C / 8);
             const unsigned grid = (unsigned)((total + 255) / 256);
+            const int cvec = o.C / 8;
+            int cshift = 0;
+            while ((1 << cshift) < cvec) ++cshift;
             if (f32)
                 wd::blend_up2_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(out), static_cast<const float*>(in),
                                                                    n_clips, o.H, o.W, o.Hy, o.Hy, o.C, 0.5f, 0.5f);
+            else if ((1 << cshift) == cvec)   // one CTA per image row, shifts instead of 64-bit divisions
+                wd::blend_up2_rows_kernel<__nv_bfloat16><<<(unsigned)(n_clips * o.H), 256, 0, st>>>(
+                    static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(in), o.H, o.W, o.Hy, o.Hy, o.C,
+                    cshift, 0.5f, 0.5f);
             else
                 wd::blend_up2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
                     static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(in), n_clips, o.H, o.W, o.Hy,

@@ -166,6 +166,49 @@ __global__ void blend_up2_kernel(T* __restrict__ x, const T* __restrict__ y, int
     store8(x + m * C + cv * 8, a);
 }
 
+// Same operation, one CTA per image row (clip, h): the 64-bit divisions of the flat-index form above were the whole cost
+// (2.4 TB/s on an HBM-bound element-wise op).  C / 8 must be a power of two (64 and 256 channels in TDN); each thread
+// walks the row's W * 8 * C / 8 vectors with shifts only and keeps two vectors in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) blend_up2_rows_kernel(T* __restrict__ x, const T* __restrict__ y, int H, int W, int Hy,
+                                                             int Wy, int C, int cshift, float alpha, float beta) {
+    const int h = blockIdx.x % H;
+    const size_t n = blockIdx.x / H;
+    const int hy = min((int)floorf(h * ((float)Hy / (float)H)), Hy - 1);
+    T* xr = x + ((n * H + h) * (size_t)W) * 8 * C;
+    const T* yr = y + ((n * Hy + hy) * (size_t)Wy) * 8 * C;
+    const int nvec = W << (3 + cshift);            // vectors of 8 channels in this row
+    const float wscale = (float)Wy / (float)W;
+    auto yoff = [&](int v) -> size_t {             // v = ((w * 8 + t) << cshift) + cv
+        const int w = v >> (3 + cshift);
+        const int wy = min((int)floorf(w * wscale), Wy - 1);
+        return ((size_t)wy << (3 + cshift)) * 8 + (size_t)(v & ((8 << cshift) - 1)) * 8;
+    };
+    int v = threadIdx.x;
+    for (; v + 256 < nvec; v += 512) {
+        float a0[8], b0[8], a1[8], b1[8];
+        load8(xr + (size_t)v * 8, a0);
+        load8(xr + (size_t)(v + 256) * 8, a1);
+        load8(yr + yoff(v), b0);
+        load8(yr + yoff(v + 256), b1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a0[q] = alpha * a0[q] + beta * b0[q];
+            a1[q] = alpha * a1[q] + beta * b1[q];
+        }
+        store8(xr + (size_t)v * 8, a0);
+        store8(xr + (size_t)(v + 256) * 8, a1);
+    }
+    if (v < nvec) {
+        float a0[8], b0[8];
+        load8(xr + (size_t)v * 8, a0);
+        load8(yr + yoff(v), b0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a0[q] = alpha * a0[q] + beta * b0[q];
+        store8(xr + (size_t)v * 8, a0);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Motion excitation.  r = C/16 (template R = 8 / 16 / 32).  fp32 scratch tensors:  bott [P, 8, r];  D [2][P, 8, r]
 // (forward / backward differences);  S2 [2][P2, 8, r] (half-resolution branch), P = clips*H*W, P2 = clips*(H/2)*(W/2).
@@ -250,11 +293,12 @@ __global__ void __launch_bounds__(kMseThreads) mse_diff_kernel(const float* __re
     const bool ok = row < rows;
     const size_t m = ok ? row : rows - 1;   // keep every lane alive for the shuffles
     const int t = (int)(m & 7);
-    size_t p = m >> 3;
-    const int w = (int)(p % W);
-    p /= W;
-    const int h = (int)(p % H);
-    const size_t n = p / H;
+    // pixel index < 2^32 (the launcher checks): 32-bit divisions — the 64-bit ones were most of this kernel's instructions
+    uint32_t p = (uint32_t)(m >> 3);
+    const int w = (int)(p % (uint32_t)W);
+    p /= (uint32_t)W;
+    const int h = (int)(p % (uint32_t)H);
+    const size_t n = p / (uint32_t)H;
     float cb[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) cb[j] = 0.0f;
@@ -342,11 +386,11 @@ __global__ void __launch_bounds__(kMseThreads) mse_small_kernel(const float* __r
     const int dir = idx >= per_dir;
     size_t m = idx - dir * per_dir;
     const int t = (int)(m & 7);
-    size_t p = m >> 3;
-    const int w2 = (int)(p % W2);
-    p /= W2;
-    const int h2 = (int)(p % H2);
-    const size_t n = p / H2;
+    uint32_t p = (uint32_t)(m >> 3);
+    const int w2 = (int)(p % (uint32_t)W2);
+    p /= (uint32_t)W2;
+    const int h2 = (int)(p % (uint32_t)H2);
+    const size_t n = p / (uint32_t)H2;
     const float* Dd = D + dir * full;
     float acc[R];
 #pragma unroll
@@ -427,9 +471,10 @@ __global__ void __launch_bounds__(kMseThreads) mse_gate_shift_kernel(const T* __
         const int pl = threadIdx.x >> 4, dir = (threadIdx.x >> 3) & 1, t = threadIdx.x & 7;
         const size_t p = p0 + pl;
         if (p < P) {
-            const int w = (int)(p % W);
-            const int h = (int)((p / W) % H);
-            const size_t n = p / ((size_t)W * H);
+            const uint32_t p32 = (uint32_t)p;
+            const int w = (int)(p32 % (uint32_t)W);
+            const int h = (int)((p32 / (uint32_t)W) % (uint32_t)H);
+            const size_t n = p32 / ((uint32_t)W * (uint32_t)H);
             const float* Dd = a.D + dir * full;
             float acc[R];
 #pragma unroll
