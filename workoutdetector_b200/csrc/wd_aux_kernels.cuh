@@ -98,6 +98,7 @@ struct PreArgs {
     float scale_y, scale_x;  // H/rh, W/rw  (torch area_pixel_compute_scale, align_corners=False)
     float in_scale;          // 1/255 (uint8 semantics) or 1 (float-promotion quirk, inference_count.py:413)
     float mean[3], stdv[3];
+    float rstd[3];           // 1 / stdv, divided on the host (IEEE, the same value the kernels used to compute per thread)
     int pitch, pad;          // output row pitch in pixels and zero columns left of the image (blockDim.x == pitch)
 };
 
@@ -341,6 +342,10 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
     return r;
 }
 
+// FAST (host-checked): row bytes are a multiple of 4 and no column's third source pixel is clamped at the right edge, so
+// the three source pixels are nine consecutive bytes at a row-independent alignment: three word loads at one base
+// address instead of three unaligned pixel loads with their own address arithmetic.
+template <bool FAST>
 __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArgs a, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t srow[];
     __shared__ float4 ytab[kPairRows * kPairGroups];   // {y0 - ya, y1 - ya, ly, -} per output row of the CTA
@@ -412,6 +417,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArg
     const uint32_t off0 = shift + (uint32_t)x0a * 3u;
     const uint32_t off1 = shift + (uint32_t)min(x0a + 1, a.W - 1) * 3u;
     const uint32_t off2 = shift + (uint32_t)min(x0a + 2, a.W - 1) * 3u;
+    const uint32_t row_w = row_b >> 2, word0 = off0 >> 2, sh0 = (off0 & 3u) * 8u;   // FAST: word pitch, first word, byte alignment
     const bool same = x0b == x0a;
     const float wa0 = 1.0f - lxa, wa1 = lxa;
     const float wb0 = same ? 1.0f - lxb : 0.0f, wb1 = same ? lxb : 1.0f - lxb, wb2 = same ? 0.0f : lxb;
@@ -426,14 +432,27 @@ __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArg
     // horizontal blend of source row (ya + yrel) at both columns: A01 = column a channels (0,1), B01 = column b channels
     // (0,1), C2 = (a.c2, b.c2)
     auto hrow = [&](int yrel, uint64_t& A01, uint64_t& B01, uint64_t& C2) {
-        const uint32_t ro = (uint32_t)yrel * row_b;
-        const uint32_t x0 = bytes3(ro + off0), x1 = bytes3(ro + off1), x2 = bytes3(ro + off2);
         // uint8 -> float: PRMT the byte under the exponent of 2^23, subtract 2^23 (exact), scale
-        uint64_t p0 = f2_pack(__uint_as_float(__byte_perm(x0, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x0, 0x4B000000u, 0x7651)));
-        uint64_t p1 = f2_pack(__uint_as_float(__byte_perm(x1, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x1, 0x4B000000u, 0x7651)));
-        uint64_t p2 = f2_pack(__uint_as_float(__byte_perm(x2, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x2, 0x4B000000u, 0x7651)));
-        uint64_t q01 = f2_pack(__uint_as_float(__byte_perm(x0, 0x4B000000u, 0x7652)), __uint_as_float(__byte_perm(x1, 0x4B000000u, 0x7652)));
-        uint64_t q2 = f2_pack(__uint_as_float(__byte_perm(x2, 0x4B000000u, 0x7652)), 8388608.0f);
+        constexpr uint32_t K23 = 0x4B000000u;
+        uint64_t p0, p1, p2, q01, q2;
+        if (FAST) {
+            const uint32_t* w = sw + (uint32_t)yrel * row_w + word0;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const uint32_t lo = __funnelshift_r(w0, w1, sh0), hi = __funnelshift_r(w1, w2, sh0), top = w2 >> sh0;   // bytes 0-3, 4-7, 8
+            p0 = f2_pack(__uint_as_float(__byte_perm(lo, K23, 0x7650)), __uint_as_float(__byte_perm(lo, K23, 0x7651)));
+            p1 = f2_pack(__uint_as_float(__byte_perm(lo, K23, 0x7653)), __uint_as_float(__byte_perm(hi, K23, 0x7650)));
+            p2 = f2_pack(__uint_as_float(__byte_perm(hi, K23, 0x7652)), __uint_as_float(__byte_perm(hi, K23, 0x7653)));
+            q01 = f2_pack(__uint_as_float(__byte_perm(lo, K23, 0x7652)), __uint_as_float(__byte_perm(hi, K23, 0x7651)));
+            q2 = f2_pack(__uint_as_float(__byte_perm(top, K23, 0x7650)), 8388608.0f);
+        } else {
+            const uint32_t ro = (uint32_t)yrel * row_b;
+            const uint32_t x0 = bytes3(ro + off0), x1 = bytes3(ro + off1), x2 = bytes3(ro + off2);
+            p0 = f2_pack(__uint_as_float(__byte_perm(x0, K23, 0x7650)), __uint_as_float(__byte_perm(x0, K23, 0x7651)));
+            p1 = f2_pack(__uint_as_float(__byte_perm(x1, K23, 0x7650)), __uint_as_float(__byte_perm(x1, K23, 0x7651)));
+            p2 = f2_pack(__uint_as_float(__byte_perm(x2, K23, 0x7650)), __uint_as_float(__byte_perm(x2, K23, 0x7651)));
+            q01 = f2_pack(__uint_as_float(__byte_perm(x0, K23, 0x7652)), __uint_as_float(__byte_perm(x1, K23, 0x7652)));
+            q2 = f2_pack(__uint_as_float(__byte_perm(x2, K23, 0x7652)), 8388608.0f);
+        }
         p0 = f2_mul(f2_add(p0, KNEG), KS);
         p1 = f2_mul(f2_add(p1, KNEG), KS);
         p2 = f2_mul(f2_add(p2, KNEG), KS);
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArg
         const float b2 = __fmaf_rn(c0, wb0, __fmaf_rn(c1, wb1, __fmul_rn(c2, wb2)));
         C2 = f2_pack(a2, b2);
     };
-    const float rs0 = 1.0f / a.stdv[0], rs1 = 1.0f / a.stdv[1], rs2 = 1.0f / a.stdv[2];
+    const float rs0 = a.rstd[0], rs1 = a.rstd[1], rs2 = a.rstd[2];
     const uint64_t NM01 = f2_pack(-a.mean[0], -a.mean[1]), NM2 = f2_pack(-a.mean[2], -a.mean[2]);
     const uint64_t RS01 = f2_pack(rs0, rs1), RS2 = f2_pack(rs2, rs2);
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -1842,6 +1842,7 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     for (int i = 0; i < 3; ++i) {
         a.mean[i] = mean[i];
         a.stdv[i] = stdv[i];
+        a.rstd[i] = 1.0f / stdv[i];
     }
     const size_t smem = (size_t)2 * W * 3 + 48;
     if (smem > 48 * 1024) return fail(WD_ERR_INVALID, "frame width %d too large for the row staging buffer", W);
@@ -1860,7 +1861,12 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     if (!f32 && !pair_off && a.scale_x <= 1.0f && a.scale_y <= 1.0f && (a.pad & 1) == 0 && (a.pitch & 1) == 0 &&
         a.pitch <= 256 && smem_pair <= 40 * 1024) {
         dim3 grid(224 / (wd::kPairRows * wd::kPairGroups), n_out);
-        wd::preprocess_u8_pair_kernel<<<grid, 256, smem_pair, st>>>(a, static_cast<__nv_bfloat16*>(out));
+        // fast path: word-aligned rows and the last column pair's third source pixel (x0 + 2) inside the row with a
+        // pixel to spare (the device recomputes x0 in the same fp32 arithmetic; the spare pixel covers any doubt)
+        const float sx_last = a.scale_x * ((float)(222 + a.left) + 0.5f) - 0.5f;
+        const bool fast = (W * 3) % 4 == 0 && (int)std::max(sx_last, 0.0f) + 3 <= W - 1;
+        if (fast) wd::preprocess_u8_pair_kernel<true><<<grid, 256, smem_pair, st>>>(a, static_cast<__nv_bfloat16*>(out));
+        else wd::preprocess_u8_pair_kernel<false><<<grid, 256, smem_pair, st>>>(a, static_cast<__nv_bfloat16*>(out));
     } else if (smem_rows <= 40 * 1024) {
         dim3 grid(224 / wd::kPreRows, n_out);
         if (f32)
