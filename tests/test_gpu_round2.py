@@ -384,8 +384,11 @@ def test_preprocess_pair_kernel_equals_rows_kernel(weights, hw, monkeypatch):
     eng = model.engine(8)
     g = torch.Generator().manual_seed(H * 7 + W)
     fr = torch.randint(0, 256, (9, H, W, 3), generator=g, dtype=torch.uint8).cuda()
-    idx = torch.tensor([0, 8, 4, -1, 1, 3, 3, 7, 2, 5, 6], dtype=torch.int32).cuda()
-    for in_scale in (1.0 / 255.0, 1.0):
+    small = torch.tensor([0, 8, 4, -1, 1, 3, 3, 7, 2, 5, 6], dtype=torch.int32)
+    # the kernel runs 8, 16 or 28 output rows per thread depending on the number of output frames (< 96, < 256, >= 256)
+    tables = [small, (torch.arange(100) * 7 % 9).int(), torch.cat([(torch.arange(299) * 5 % 9).int(), torch.tensor([-1], dtype=torch.int32)])]
+    for idx, in_scale in [(tables[0], 1.0 / 255.0), (tables[0], 1.0), (tables[1], 1.0 / 255.0), (tables[2], 1.0 / 255.0)]:
+        idx = idx.cuda()
         monkeypatch.setenv("WD_PRE_PAIR", "1")
         new = eng.preprocess_u8(fr, idx, in_scale=in_scale).clone()
         monkeypatch.setenv("WD_PRE_PAIR", "0")

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_rows_kernel(const PreArgs a
 // 224 -> 256 -> crop 224 of the headline workload).  ncu on the rows kernel above (profiles/r02_ncu_full_top_kernels.txt):
 // issue slots 85 % busy, 1014 executed instructions per thread — the fully unrolled, predicated row loop computes all
 // 16 candidate source-row blends per thread.  Here:
-//   * one thread owns TWO adjacent output columns for kPairRows rows: with scale <= 1 their four horizontal taps are
+//   * one thread owns TWO adjacent output columns for ROWS rows: with scale <= 1 their four horizontal taps are
 //     three consecutive source pixels, converted once (PRMT under the exponent of 2^23, then packed fp32 arithmetic:
 //     add/mul/fma.f32x2 — two lanes per issue slot, each lane IEEE-rounded exactly like the scalar instruction);
 //   * the row loop is a real loop with warp-uniform branches: a source row's horizontal blend is computed once and
@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(256) preprocess_u8_rows_kernel(const PreArgs a
 // The arithmetic per value is the one of the kernels above: ((b*in_scale)*(1-lx) + (b'*in_scale)*lx) blended
 // vertically the same way, then (v - mean) * (1/std).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPairRows = 8;      // output rows per thread
+// output rows per thread: template parameter ROWS (8 / 16 / 28 — the per-thread set-up and the source rows shared by
+// neighbouring output rows are amortised over more rows; fewer, longer CTAs need a larger launch to fill the GPU)
 constexpr int kPairGroups = 2;    // row groups per CTA (256 threads = 2 x 128 column-pair threads)
 
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
@@ -345,11 +346,11 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
 // FAST (host-checked): row bytes are a multiple of 4 and no column's third source pixel is clamped at the right edge, so
 // the three source pixels are nine consecutive bytes at a row-independent alignment: three word loads at one base
 // address instead of three unaligned pixel loads with their own address arithmetic.
-template <bool FAST>
+template <bool FAST, int ROWS>
 __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArgs a, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t srow[];
-    __shared__ float4 ytab[kPairRows * kPairGroups];   // {y0 - ya, y1 - ya, ly, -} per output row of the CTA
-    constexpr int kRows = kPairRows * kPairGroups;
+    __shared__ float4 ytab[ROWS * kPairGroups];   // {y0 - ya, y1 - ya, ly, -} per output row of the CTA
+    constexpr int kRows = ROWS * kPairGroups;
     const int oy0 = blockIdx.x * kRows;
     const int f = blockIdx.y;
     const int src = a.src_index ? a.src_index[f] : f;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArg
     const int ox = col - a.pad;                        // pad is even: both columns are inside the image or both outside
     const bool active = col < a.pitch;
     const bool inside = (unsigned)ox < 224u;
-    __nv_bfloat16* o = out + (((size_t)f * 224 + oy0 + group * kPairRows) * a.pitch + col) * 4;
+    __nv_bfloat16* o = out + (((size_t)f * 224 + oy0 + group * ROWS) * a.pitch + col) * 4;
     const size_t orow = (size_t)a.pitch * 4;
     if (src < 0) {  // zero raw frame: (0*in_scale - mean) / std
         if (active) {
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArg
             const uint32_t w0 = inside ? *reinterpret_cast<const uint32_t*>(&lo) : 0u;
             const uint32_t w1 = inside ? *reinterpret_cast<const uint32_t*>(&hi) : 0u;
 #pragma unroll
-            for (int r = 0; r < kPairRows; ++r) *reinterpret_cast<uint4*>(o + r * orow) = make_uint4(w0, w1, w0, w1);
+            for (int r = 0; r < ROWS; ++r) *reinterpret_cast<uint4*>(o + r * orow) = make_uint4(w0, w1, w0, w1);
         }
         return;
     }
@@ -476,14 +477,14 @@ __global__ void __launch_bounds__(256, 6) preprocess_u8_pair_kernel(const PreArg
     if (!active) return;
     if (!inside) {
 #pragma unroll
-        for (int r = 0; r < kPairRows; ++r) *reinterpret_cast<uint4*>(o + r * orow) = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = 0; r < ROWS; ++r) *reinterpret_cast<uint4*>(o + r * orow) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     int py0 = -1, py1 = -1;                     // source rows (relative) the carried blends belong to
     uint64_t tA = 0, tB = 0, tC = 0, bA = 0, bB = 0, bC = 0;
 #pragma unroll 1
-    for (int r = 0; r < kPairRows; ++r) {
-        const float4 yt4 = ytab[group * kPairRows + r];
+    for (int r = 0; r < ROWS; ++r) {
+        const float4 yt4 = ytab[group * ROWS + r];
         const int y0 = __float_as_int(yt4.x), y1 = __float_as_int(yt4.y);
         const float ly = yt4.z;
         // warp-uniform reuse of the carried blends (up-scaling: y0 advances by 0 or 1 per output row)

@@ -1853,20 +1853,27 @@ int preprocess_impl(int mode, const uint8_t* frames, int n_src, int H, int W, co
     // rows of the source a band of kPreRows output rows can touch (+2 for the bilinear neighbour and rounding)
     const size_t band_rows = (size_t)std::ceil(wd::kPreRows * a.scale_y) + 2;
     const size_t smem_rows = band_rows * W * 3 + 64;  // + alignment shift, 16-byte rounding and the word over-read
-    // product path without shrinking (the headline 224 -> 256 -> crop 224): two columns per thread, packed fp32
-    const size_t band_pair = (size_t)std::ceil(wd::kPairRows * wd::kPairGroups * a.scale_y) + 2;
+    // product path without shrinking (the headline 224 -> 256 -> crop 224): two columns per thread, packed fp32.
+    // Rows per thread by launch size: 28 (4 CTAs per frame) from 256 frames on, 16 from 96, else 8 — 512 frames take
+    // 75 / 65.5 / 62.7 us with 8 / 16 / 28 rows; small launches need the CTAs.
+    const int pair_rows = n_out >= 256 ? 28 : (n_out >= 96 ? 16 : 8);
+    const size_t band_pair = (size_t)std::ceil(pair_rows * wd::kPairGroups * a.scale_y) + 2;
     const size_t smem_pair = band_pair * W * 3 + 64;
     const char* pair_env = getenv("WD_PRE_PAIR");   // 0: the rows kernel (differential tests)
     const bool pair_off = pair_env && atoi(pair_env) == 0;
     if (!f32 && !pair_off && a.scale_x <= 1.0f && a.scale_y <= 1.0f && (a.pad & 1) == 0 && (a.pitch & 1) == 0 &&
         a.pitch <= 256 && smem_pair <= 40 * 1024) {
-        dim3 grid(224 / (wd::kPairRows * wd::kPairGroups), n_out);
+        dim3 grid(224 / (pair_rows * wd::kPairGroups), n_out);
         // fast path: word-aligned rows and the last column pair's third source pixel (x0 + 2) inside the row with a
         // pixel to spare (the device recomputes x0 in the same fp32 arithmetic; the spare pixel covers any doubt)
         const float sx_last = a.scale_x * ((float)(222 + a.left) + 0.5f) - 0.5f;
         const bool fast = (W * 3) % 4 == 0 && (int)std::max(sx_last, 0.0f) + 3 <= W - 1;
-        if (fast) wd::preprocess_u8_pair_kernel<true><<<grid, 256, smem_pair, st>>>(a, static_cast<__nv_bfloat16*>(out));
-        else wd::preprocess_u8_pair_kernel<false><<<grid, 256, smem_pair, st>>>(a, static_cast<__nv_bfloat16*>(out));
+        __nv_bfloat16* o16 = static_cast<__nv_bfloat16*>(out);
+#define WD_PAIR_LAUNCH(F, R) wd::preprocess_u8_pair_kernel<F, R><<<grid, 256, smem_pair, st>>>(a, o16)
+        if (pair_rows == 28) { if (fast) WD_PAIR_LAUNCH(true, 28); else WD_PAIR_LAUNCH(false, 28); }
+        else if (pair_rows == 16) { if (fast) WD_PAIR_LAUNCH(true, 16); else WD_PAIR_LAUNCH(false, 16); }
+        else { if (fast) WD_PAIR_LAUNCH(true, 8); else WD_PAIR_LAUNCH(false, 8); }
+#undef WD_PAIR_LAUNCH
     } else if (smem_rows <= 40 * 1024) {
         dim3 grid(224 / wd::kPreRows, n_out);
         if (f32)
