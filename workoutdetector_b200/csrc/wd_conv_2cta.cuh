@@ -102,10 +102,12 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 // Shared-memory plan: a stage is this CTA's A tile (16 KiB) + its half of the W tile (BN/2 rows).  RES keeps three
 // in-place residual/output slabs per epilogue warp (8 x 3 x 4 KiB), otherwise two output slabs per warp; the stages
 // take what is left of the 227 KiB (BN 256: 4 / 5 stages, BN 128: 5 / 6).
-template <int BN, bool RES>
+// SLABS = 1 (no residual, long K: conv1 of layers 3-4): ONE output slab per warp — the epilogue of a K >= 512 tile has time
+// to wait for its previous store — which buys a sixth stage (more bytes in flight per SM on an HBM/L2-latency-bound feed).
+template <int BN, bool RES, int SLABS = 0>
 struct Plan2Cta {
     static constexpr int kStage = kATileBytes + (BN / 2) * kTileK * 2;
-    static constexpr int kSlabsPerWarp = RES ? 3 : 2;
+    static constexpr int kSlabsPerWarp = SLABS ? SLABS : (RES ? 3 : 2);
     static constexpr int kStages = (232448 - 3072 - 8 * kSlabsPerWarp * kEpiSlab) / kStage > 6
                                        ? 6 : (232448 - 3072 - 8 * kSlabsPerWarp * kEpiSlab) / kStage;
     static constexpr int kOffOut = kStages * kStage;
@@ -133,12 +135,13 @@ struct Conv2CtaArgs {
 // TAP = true : A_TAP geometry (3x3 / 1x1, stride 1 or 2): the CTA's tile is 14 output pixels (112 rows), every
 //              (tap, channel block) k-block is one or two strided 5-D boxes; a pair computes two consecutive tiles.
 // RES: residual added in place in the slab the TMA load delivered it to (as the 8-warp epilogue of conv_v4_kernel).
-template <int BN, bool TAP, bool RES>
+template <int BN, bool TAP, bool RES, int SLABS = 0>
 __global__ void __launch_bounds__(384, 1)
 conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_constant__ CUtensorMap amap,
                  const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
                  const __grid_constant__ CUtensorMap rmap, const Conv2CtaArgs a) {
-    using P = Plan2Cta<BN, RES>;
+    using P = Plan2Cta<BN, RES, SLABS>;
+    static_assert(SLABS == 0 || (SLABS == 1 && !RES), "one-slab epilogue: no residual");
     constexpr int k2cStage = P::kStage;
     constexpr int k2cStages = P::kStages;
     constexpr int kCpw = BN / 128;  // 64-column chunks per epilogue warp
@@ -241,11 +244,14 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
             tc_fence_after_sync();
 #pragma unroll 1
             for (int c = kCpw * half; c < kCpw * half + kCpw; ++c, ++chunk_idx) {
-                const uint32_t slot = RES ? chunk_idx % 3 : (chunk_idx & 1);
+                const uint32_t slot = RES ? chunk_idx % 3 : (SLABS == 1 ? 0u : (chunk_idx & 1));
                 uint8_t* obuf = my_out + slot * kEpiSlab + row_off;
                 if (RES) mbar_wait(&my_bar[slot], (chunk_idx / 3) & 1);  // residual chunk has landed in its slab
                 else {
-                    if (elect_one()) tma_store_wait_read1();  // the store that last read this slab is done reading
+                    if (elect_one()) {   // the store that last read this slab is done reading
+                        if (SLABS == 1) tma_store_wait_read();
+                        else tma_store_wait_read1();
+                    }
                     __syncwarp();
                 }
 #pragma unroll

@@ -45,6 +45,8 @@ struct ConvArgs3 {
     int tap_bh;      // tap mode: image rows per tile (2 for 7-pixel rows, else 1)
     int prefetch_kblocks;  // v4: L2-prefetch the A operand this many k-blocks ahead (0 = off)
     uint32_t* trace;       // v4 debug: CTA 0 writes clock() samples of its pipeline roles here (nullable)
+    int tma_fix;           // v4 gather mode, 1x1 / 64 channels / fold 8 (layer1.0.conv1): the tile arrives as ONE TMA box and the
+                           // producer warps apply the TemporalShift of channels 0..15 in shared memory (see conv_v4_kernel)
 };
 
 #ifdef WD_LEGACY_KERNELS  // third generation (W-resident, strip 3x3): differential-test builds only

@@ -122,7 +122,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         if (elect_one()) {
             tma_prefetch_desc(&wmap);
             tma_prefetch_desc(&omap);
-            if (kTmaA) tma_prefetch_desc(&amap);
+            if (kTmaA || (AMODE == A_GATHER && p.tma_fix)) tma_prefetch_desc(&amap);
             if (HAS_RES) tma_prefetch_desc(&rmap);
             if (k112) tma_prefetch_desc(&omap16);
             if ((AMODE == A_TMA && (a.fold == 32 || p.kb_split > 0)) || (kTap && p.kb_split > 0)) tma_prefetch_desc(&amap32);
@@ -614,6 +614,49 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
         // A gather producers (warps 6-9): 16-byte cp.async with zero fill into the swizzled A stage
         // ==========================================================================================
         const int ptid = tid - 192;
+        if (AMODE == A_GATHER && p.tma_fix) {
+            // layer1.0.conv1 (1x1, 64 channels = one k-block, TemporalShift fold 8): the un-shifted 128 x 128 B tile
+            // arrives as ONE TMA box {64, 8, 16}; the shift moves 16 bytes of a row (channels 0..7) up from segment
+            // t+1 and 16 bytes (channels 8..15) down from t-1, and the 8 segments of a pixel are the 8 rows of one
+            // 1024-byte swizzle atom: producer thread r rewrites two 16-byte cells of row r from its neighbours in the
+            // same atom (same warp: read, __syncwarp, write).  The gather form of this layer issues 1024 cp.async of
+            // 16 bytes per tile instead (profiles/r02_op_times_*: 100 us against 65 us for the plain TMA feed).
+            uint64_t* a_tma = bars + 16;   // [8] TMA landing barriers (the streamed-W barriers are unused: W is resident)
+            const int S = p.a_stages;
+            const int ahead = S > 2 ? S - 2 : 1;
+            const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int row = ptid, t = row & 7;
+            const uint32_t src0 = (uint32_t)(row + 1) * 128u + (uint32_t)((0 ^ ((row + 1) & 7)) << 4);   // channels 0..7 of t+1
+            const uint32_t src1 = (uint32_t)(row - 1) * 128u + (uint32_t)((1 ^ ((row - 1) & 7)) << 4);   // channels 8..15 of t-1
+            const uint32_t dst0 = (uint32_t)row * 128u + (uint32_t)((0 ^ t) << 4);
+            const uint32_t dst1 = (uint32_t)row * 128u + (uint32_t)((1 ^ t) << 4);
+            auto issue = [&](int i) {   // warp 6: request tile i of this CTA into ring slot i % S
+                const int slot = i % S;
+                mbar_wait(&a_empty[slot], ((i / S) & 1) ^ 1);
+                if (elect_one()) {
+                    const int m_tile = ((int)blockIdx.x + i * (int)gridDim.x) / a.n_tiles;
+                    mbar_arrive_expect_tx(&a_tma[slot], kATileBytes);
+                    tma_load_3d(&amap, &a_tma[slot], sA + slot * p.a_stage_bytes, 0, 0, (m_tile * kTileM) >> 3);
+                }
+                __syncwarp();
+            };
+            if (warp == 6)
+                for (int i = 0; i < ahead && i < my_tiles; ++i) issue(i);
+            for (int it = 0; it < my_tiles; ++it) {
+                if (warp == 6 && it + ahead < my_tiles) issue(it + ahead);
+                const int slot = it % S;
+                mbar_wait(&a_tma[slot], (it / S) & 1);
+                uint8_t* st = sA + slot * p.a_stage_bytes;
+                uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+                if (t < 7) v0 = *reinterpret_cast<const uint4*>(st + src0);
+                if (t > 0) v1 = *reinterpret_cast<const uint4*>(st + src1);
+                __syncwarp();
+                *reinterpret_cast<uint4*>(st + dst0) = v0;
+                *reinterpret_cast<uint4*>(st + dst1) = v1;
+                fence_proxy_async_smem();
+                mbar_arrive(&a_full[slot]);
+            }
+        } else {
         const int j = ptid & 7;
         const int rsub = ptid >> 3;
         const int t = rsub & 7;
@@ -682,6 +725,7 @@ conv_v4_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__
                 }
                 cp_async_mbar_arrive_noinc(&a_full[slot]);
             }
+        }
         }
     }
 

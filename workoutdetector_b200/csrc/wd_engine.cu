@@ -169,6 +169,7 @@ struct ConvLayer {
     CUtensorMap amap9;   // 7 x 7 strip mode: {C, T, W, H, clips} view, box {64, 8, 9, 1, 1}
     bool has_strip7 = false;   // 3x3 stride-1 convolution on 7 x 7 images: conv_2cta_strip_kernel<256, true>
     bool has_s2 = false;
+    bool tma_fix = false;  // gather-mode 1x1 / 64 channels / fold 8: one TMA box per tile + TemporalShift fix-up in shared memory
 };
 
 // TDN motion excitation + temporal Conv1d of one BottleneckShift (tdn.py:188-334, 339-376); all fp32 on device
@@ -862,6 +863,7 @@ uint32_t* g_trace = nullptr;  // debug timeline buffer (WD_TRACE=<file> with the
 // engine-less single-layer hooks)
 int g_prefetch_kblocks = getenv("WD_PREFETCH_KBLOCKS") ? atoi(getenv("WD_PREFETCH_KBLOCKS")) : -1;  // -1 = per-layer rule
 
+int g_tma_fix = getenv("WD_TMA_FIX") ? atoi(getenv("WD_TMA_FIX")) : 1;   // layer1.0.conv1: TMA tile + in-smem shift fix-up instead of the cp.async gather
 int g_tap = getenv("WD_TAP") ? atoi(getenv("WD_TAP")) : 1;              // A_TAP mode for stride-2 / 7x7 convolutions
 int g_fold32_tma = getenv("WD_FOLD32") ? atoi(getenv("WD_FOLD32")) : 1;  // fold-32 conv1 through TMA (two SWIZZLE_64B halves)
 int g_w_group = getenv("WD_WGROUP") ? atoi(getenv("WD_WGROUP")) : 1;    // group W steps of narrow strip tiles
@@ -905,6 +907,7 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
     p.prefetch_kblocks = (g_prefetch_kblocks >= 0) ? g_prefetch_kblocks : ((sp.a_stages <= 3 && a.kblocks >= 4) ? 4 : 0);
     p.trace = g_trace;
+    p.tma_fix = (AMODE == wd::A_GATHER && c.tma_fix && !RES && a.M % wd::kTileM == 0 && sp.w_resident && sp.a_stages >= 3) ? 1 : 0;
     const unsigned threads = wd::kThreadsFor<AMODE, EPI8>;
     WD_CUDA(launch_pdl(kfn, (unsigned)grid, threads, (size_t)sp.total, st, c.wmap, c.amap, c.omap, c.rmap, c.omap16,
                        c.amap32, p));
@@ -956,11 +959,11 @@ bool eligible_2cta(const ConvLayer& c, const wd::ConvArgs& a) {
     return g_2cta >= 3 && c.a_mode == wd::A_TAP && a.kblocks >= tap_min_kb;   // stride-2 / 7x7 convolutions of layers 3-4
 }
 
-template <int BN, bool TAP, bool RES>
+template <int BN, bool TAP, bool RES, int SLABS = 0>
 int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = wd::conv_2cta_kernel<BN, TAP, RES>;
-    constexpr int smem = wd::Plan2Cta<BN, RES>::kSmem;
+    auto kfn = wd::conv_2cta_kernel<BN, TAP, RES, SLABS>;
+    constexpr int smem = wd::Plan2Cta<BN, RES, SLABS>::kSmem;
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -1005,8 +1008,11 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
 int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     if (c.tile_n == 128) return launch_2cta_t<128, true, false>(c, a, sm_count, st);
     if (a.residual != nullptr) return launch_2cta_t<256, false, true>(c, a, sm_count, st);
-    return c.a_mode == wd::A_TAP ? launch_2cta_t<256, true, false>(c, a, sm_count, st)
-                                 : launch_2cta_t<256, false, false>(c, a, sm_count, st);
+    if (c.a_mode == wd::A_TAP) return launch_2cta_t<256, true, false>(c, a, sm_count, st);
+    // conv1 of layers 3-4 (K >= 512): one output slab per epilogue warp, six stages instead of five
+    static const int slab1_min_kb = getenv("WD_2CTA_SLAB1") ? atoi(getenv("WD_2CTA_SLAB1")) : 8;   // 0 = off
+    if (slab1_min_kb > 0 && a.kblocks >= slab1_min_kb) return launch_2cta_t<256, false, false, 1>(c, a, sm_count, st);
+    return launch_2cta_t<256, false, false>(c, a, sm_count, st);
 }
 
 // Tail split of the pair strip kernel (Conv2CtaStripArgs): the tiles of the last, partial wave are cut into 2 or 4
@@ -1079,9 +1085,10 @@ int launch_2cta_strip(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, c
 // CTA tile) and the stride-2 3x3 convolutions of layers 3-4 (conv_2cta_strip_kernel<256, 2>) on the pair strip kernel
 // instead of tap boxes.  WD_STRIP7=0 keeps the tap-mode pair kernel for all of them, 1 = stride 1 only, 2 = both.
 int g_strip7 = getenv("WD_STRIP7") ? atoi(getenv("WD_STRIP7")) : 2;
-template <int MODE>   // 1: 7 x 7 images, stride 1 (two image rows per tile); 2: stride 2 (row boxes + stride in the MMA descriptor)
+// WD_S2_PAIR128=1: layer2.0.conv2 (128 -> 128, stride 2) on the pair kernel too (BN = 128) instead of conv_strip2d_kernel
+int g_s2_pair128 = getenv("WD_S2_PAIR128") ? atoi(getenv("WD_S2_PAIR128")) : 0;
+template <int MODE, int BN = 256>   // 1: 7 x 7 images, stride 1 (two image rows per tile); 2: stride 2 (row boxes + stride in the MMA descriptor)
 int launch_2cta_strip_mode(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
-    constexpr int BN = 256;
     static bool configured = false;
     auto kfn = wd::conv_2cta_strip_kernel<BN, MODE>;
     if (!configured) {
@@ -1106,7 +1113,7 @@ int launch_2cta_strip_mode(const ConvLayer& c, const wd::ConvArgs& a, int sm_cou
     const int whalf = (BN / 2) * 128;
     const int a_bytes = MODE == 2 ? 3 * 33 * 1024 : 2 * 3 * 18 * 1024;
     const int fixed = a_bytes + 8 * wd::kEpiSlab + 2048 + 1024;
-    p.w_stages = std::min(8, (232448 - fixed) / whalf);
+    p.w_stages = std::min(BN == 128 ? 16 : 8, (232448 - fixed) / whalf);
     p.w_resident = 0;
     p.off_w = a_bytes;
     p.off_out = p.off_w + p.w_stages * whalf;
@@ -1211,6 +1218,8 @@ int launch_strip2d(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cuda
 }
 
 int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st) {
+    if (g_s2_pair128 && g_2cta >= 3 && c.has_strip7 && c.stride == 2 && c.tile_n == 128 && a.residual == nullptr && a.fold == 0)
+        return launch_2cta_strip_mode<2, 128>(c, a, sm_count, st);
     if (g_strip2 >= 3 && c.has_s2 && a.residual == nullptr && c.kb_split == 0) return launch_strip2d(c, a, sm_count, st);
     if (g_strip2 >= 2 && c.a_mode == wd::A_STRIP && c.tile_n == 128 && c.Cout == 128 && a.residual == nullptr &&
         a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
@@ -2170,6 +2179,12 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                     WD_TRY(make_omap(&c.omap24, e->buf[o.out_buf], c.Cout, rows, 24));
                     c.has_strip7 = true;
                 }
+                if (g_s2_pair128 && c.k == 3 && c.stride == 2 && c.Wout % wd::kStripPixels == 0 && c.Win == 2 * c.Wout &&
+                    c.Hin == 2 * c.Hout && c.tile_n == 128 && c.Cout == 128 && c.Cin % 64 == 0 && c.fold == 0 &&
+                    o.res_buf < 0 && c.kb_split == 0 && !c.s2d) {   // layer2.0.conv2 on the pair kernel (BN = 128)
+                    WD_TRY(make_amap9(&c.amap9, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips, 29));
+                    c.has_strip7 = true;
+                }
                 if (o.in2_buf >= 0) {  // fused stride-2 downsample: the block input at twice the resolution
                     const ConvLayer& d = e->convs[c.fuse_ds];
                     WD_TRY(make_amap_tap(&c.amap32, e->buf[o.in2_buf], d.Cin, d.Win, d.Hin, (size_t)e->desc.max_clips,
@@ -2182,6 +2197,11 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                 WD_TRY(make_amap5(&c.amap_s2, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
                 WD_TRY(make_omap(&c.omap24, e->buf[o.out_buf], c.Cout, rows, 24));
                 c.has_s2 = true;
+            }
+            if (g_tma_fix && c.a_mode == wd::A_GATHER && c.k == 1 && c.stride == 1 && c.Cin == 64 && c.fold == 8 &&
+                c.tile_n == 64 && o.in_buf >= 0 && o.res_buf < 0 && c.kb_split == 0 && !c.stem) {   // layer1.0.conv1
+                WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
+                c.tma_fix = true;
             }
             if (c.a_mode != wd::A_TMA) continue;
             WD_TRY(make_amap(&c.amap, e->buf[o.in_buf], c.Cin, (size_t)e->desc.max_clips * c.Hin * c.Win));
@@ -2621,6 +2641,11 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
         rc = fail(WD_ERR_INVALID, "shape not eligible for the requested A-operand path");
     } else {
         if (a_mode != wd::A_TMA && a_mode != wd::A_STRIP && a_mode != wd::A_TAP) c.a_mode = wd::A_GATHER;
+        if (g_tma_fix && c.a_mode == wd::A_GATHER && ksize == 1 && stride == 1 && Cin == 64 && fold == 8 && c.tile_n == 64 &&
+            !residual && persistent >= 3) {
+            rc = make_amap(&c.amap, x, Cin, (size_t)clips * Hin * Win);
+            c.tma_fix = rc == WD_OK;
+        }
         if (c.a_mode == wd::A_TMA) rc = make_amap(&c.amap, x, Cin, (size_t)clips * Hin * Win);
         if (c.a_mode == wd::A_TMA && fold == 32 && rc == WD_OK) rc = make_amap32(&c.amap32, x, Cin, (size_t)clips * Hin * Win);
         if (c.a_mode == wd::A_TAP) {
@@ -2637,6 +2662,11 @@ static int debug_conv_impl(const void* x, const float* w, const float* bias, con
                 !residual) {
                 rc = make_amap9(&c.amap9, x, Cin, Win, Hin, (size_t)clips, c.Wout == 7 ? 15 : 29);
                 if (rc == WD_OK) rc = make_omap(&c.omap24, y, Cout, (size_t)clips * c.Hout * c.Wout * 8, 24);
+                c.has_strip7 = rc == WD_OK;
+            }
+            if (rc == WD_OK && g_s2_pair128 && ksize == 3 && stride == 2 && c.Wout % wd::kStripPixels == 0 && Win == 2 * c.Wout &&
+                Hin == 2 * c.Hout && c.tile_n == 128 && Cout == 128 && Cin % 64 == 0 && fold == 0 && !residual) {
+                rc = make_amap9(&c.amap9, x, Cin, Win, Hin, (size_t)clips, 29);
                 c.has_strip7 = rc == WD_OK;
             }
         }
