@@ -1008,9 +1008,13 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
 int launch_2cta(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     if (c.tile_n == 128) return launch_2cta_t<128, true, false>(c, a, sm_count, st);
     if (a.residual != nullptr) return launch_2cta_t<256, false, true>(c, a, sm_count, st);
-    if (c.a_mode == wd::A_TAP) return launch_2cta_t<256, true, false>(c, a, sm_count, st);
     // conv1 of layers 3-4 (K >= 512): one output slab per epilogue warp, six stages instead of five
     static const int slab1_min_kb = getenv("WD_2CTA_SLAB1") ? atoi(getenv("WD_2CTA_SLAB1")) : 8;   // 0 = off
+    static const int slab1_tap_min_kb = getenv("WD_2CTA_SLAB1_TAP") ? atoi(getenv("WD_2CTA_SLAB1_TAP")) : 6;   // 0 = off; conv3 + stride-2 downsample of block 0 in layers 2-4: -2..-4 us each
+    if (c.a_mode == wd::A_TAP) {
+        if (slab1_tap_min_kb > 0 && a.kblocks >= slab1_tap_min_kb) return launch_2cta_t<256, true, false, 1>(c, a, sm_count, st);
+        return launch_2cta_t<256, true, false>(c, a, sm_count, st);
+    }
     if (slab1_min_kb > 0 && a.kblocks >= slab1_min_kb) return launch_2cta_t<256, false, false, 1>(c, a, sm_count, st);
     return launch_2cta_t<256, false, false>(c, a, sm_count, st);
 }

@@ -390,20 +390,23 @@ stem_pool2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                 const int acc = tile_iter & 1;
                 mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
                 tc_fence_after_sync();
-#pragma unroll 1
+                // both conv rows of the buffer are read before either is processed: the accumulator goes back to the MMA
+                // issuer one row's worth of pooling earlier (the epilogue is this kernel's critical path)
+                uint32_t vboth[2][32];
+                {
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + half * 32;
+                    tmem_ld32(taddr, vboth[0]);
+                    tmem_ld32(taddr + 64, vboth[1]);
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+                    __syncwarp();
+                }
+#pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int oh = oh0 + c;
-                    const uint32_t taddr =
-                        tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + c * 64 + half * 32;
-                    uint32_t v[32];
-                    tmem_ld32(taddr, v);
-                    tmem_ld_wait();
-                    if (c == 1) {
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
-                        __syncwarp();
-                    }
+                    const uint32_t* v = vboth[c];
                     if (oh > oh_hi) continue;   // the extra row of an odd-sized unit
                     uint32_t cur[16];
 #pragma unroll
