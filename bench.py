@@ -207,17 +207,18 @@ def run_reference(args, rank):
 # roofline object shared by the workloads
 # ----------------------------------------------------------------------------------------------------------------
 def roofline_of(clips_per_s_per_gpu, arch, clocks, eng=None, frames=None, B=None, step_ms=None):
-    """Whole-step achieved TFLOP/s against the measured bf16 peak.  The burst figure is the denominator whenever the SM
-    clock sampled under load sits at its maximum (the sustained figure was measured at a 1350 MHz median); the other
-    one is reported beside it.  With an engine, per-launch CUDA-event times of the tcgen05 launches are added — scaled
-    to the un-bracketed step, because bracketing every launch with events defeats programmatic dependent launch."""
+    """Whole-step achieved TFLOP/s against the measured BURST bf16 peak (the conservative denominator, whatever the SM
+    clock sampled under load was: the 1000 W cap pulls it to 1.65-1.8 GHz within ~100 ms of this workload); the figure
+    against the sustained peak (measured at a 1350 MHz median) is reported beside it.  With an engine, per-launch
+    CUDA-event times of the tcgen05 launches are added — scaled to the un-bracketed step, because bracketing every
+    launch with events defeats programmatic dependent launch."""
     peaks = load_peaks()
     tf = clips_per_s_per_gpu * GFLOP_PER_CLIP[arch] / 1e3
     at_max = bool(clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
-    denom = "burst" if at_max or not clocks.get("sm_mhz") else "sustained"
+    denom = "burst"
     r = dict(bound="tensor", achieved=tf, peak=peaks[denom], unit="TFLOP/s", frac=tf / peaks[denom], traffic=None,
              peak_kind=f"{denom} bf16, {peaks['source']}", frac_of_burst=tf / peaks["burst"],
-             frac_of_sustained=tf / peaks["sustained"],
+             frac_of_sustained=tf / peaks["sustained"], sm_clock_at_max=at_max,
              scope="whole step: every kernel of the step (preprocess, stem, convolutions, head, counter) over the "
                    f"algorithmic {GFLOP_PER_CLIP[arch]} GFLOP per clip",
              formula="value / n_gpus * GFLOP_per_clip / 1e3 / peak")

@@ -404,11 +404,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int N2>
+// RES = false (block 0 of layer 1: the downsample rides in K1 = [y2 | x], k-blocks >= kb_split come from `amap2`): no
+// residual loads, two output slabs per warp instead of three (the shared memory goes to W1's second k-block).
+template <int N2, bool RES = true>
 __global__ void __launch_bounds__(kF2eThreads, 1)
 conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], box {64, 256}
                    const __grid_constant__ CUtensorMap w2map,   // [N2, 256], box {64, N2}
                    const __grid_constant__ CUtensorMap amap,    // y2 {64, 8, P}
+                   const __grid_constant__ CUtensorMap amap2,   // block input {64, 8, P} (fused downsample) or unused
                    const __grid_constant__ CUtensorMap omap,    // y  [rows, 256], box {64, 32}
                    const __grid_constant__ CUtensorMap rmap,    // residual, same geometry
                    const __grid_constant__ CUtensorMap zmap,    // z  [rows, N2],  box {64, 32}
@@ -418,7 +421,8 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
     uint8_t* sA = smem;
     uint8_t* sW1 = smem + a.off_w1;
     uint8_t* sW2 = smem + a.off_w2;
-    uint8_t* sOut = smem + a.off_out;        // 8 warps x 3 slabs x 4 KiB
+    constexpr uint32_t kSl = RES ? 3u : 2u;   // slabs per epilogue warp
+    uint8_t* sOut = smem + a.off_out;        // 8 warps x kSl slabs x 4 KiB
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
     uint64_t* a_full = bars;               // [8]
     uint64_t* a_empty = bars + 8;          // [8]
@@ -443,7 +447,8 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
             tma_prefetch_desc(&amap);
             tma_prefetch_desc(&omap);
             tma_prefetch_desc(&zmap);
-            tma_prefetch_desc(&rmap);
+            if (RES) tma_prefetch_desc(&rmap);
+            if (a.kb_split > 0) tma_prefetch_desc(&amap2);
             for (int s = 0; s < 8; ++s) {
                 mbar_init(&a_full[s], 1);
                 mbar_init(&a_empty[s], 1);
@@ -472,7 +477,7 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
 
     if (warp < 8) {
         const int quarter = warp & 3, half = warp >> 2;
-        uint8_t* my_slab = sOut + warp * 3 * kEpiSlab;
+        uint8_t* my_slab = sOut + warp * kSl * kEpiSlab;
         uint64_t* my_res_bar = res_bar + warp * 3;
         const uint32_t row_off = lane * 128;
         const uint32_t sw = lane & 7;
@@ -492,6 +497,7 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
         // free once the store of position r - 3 has been read; at the end of unit n (store n committed, wait_group.read 1
         // done) that holds for every r <= n + 2.
         auto request_upto = [&](uint32_t limit) {
+            if (!RES) return;
             while ((int)req_ti < my_tiles && req_n <= limit) {
                 const int t2 = (int)blockIdx.x + (int)req_ti * (int)gridDim.x;
                 const uint32_t slot = req_n % 3u;
@@ -520,14 +526,16 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
 #pragma unroll 1
             for (int i = 0; i < 2; ++i, ++n) {
                 const int c = y_chunk(i);
-                const uint32_t slot = n % 3u;
+                const uint32_t slot = n % kSl;
                 uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
                 uint32_t v0[32], v1[32];
                 tmem_ld32(tacc + c * 64, v0);
                 tmem_ld32(tacc + c * 64 + 32, v1);
-                const uint32_t uses = slot == 0 ? res_uses[0] : (slot == 1 ? res_uses[1] : res_uses[2]);
-                mbar_wait(&my_res_bar[slot], uses & 1u);
-                if (slot == 0) ++res_uses[0]; else if (slot == 1) ++res_uses[1]; else ++res_uses[2];
+                if (RES) {
+                    const uint32_t uses = slot == 0 ? res_uses[0] : (slot == 1 ? res_uses[1] : res_uses[2]);
+                    mbar_wait(&my_res_bar[slot], uses & 1u);
+                    if (slot == 0) ++res_uses[0]; else if (slot == 1) ++res_uses[1]; else ++res_uses[2];
+                }
                 tmem_ld_wait();
                 // chunks 0 and 1 (this quarter's first units) have left tensor memory: from here on either warp may write
                 // packed columns over the other's accumulator columns
@@ -539,16 +547,18 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                     const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
                     const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
                     uint4* cell = reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4));
-                    const uint4 rq = *cell;
                     float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
                                   __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
                                   __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
                                   __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
-                    const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+                    if (RES) {
+                        const uint4 rq = *cell;
+                        const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        f[2 * e] += __uint_as_float(rw[e] << 16);
-                        f[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                        for (int e = 0; e < 4; ++e) {
+                            f[2 * e] += __uint_as_float(rw[e] << 16);
+                            f[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                        }
                     }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) pk[q * 4 + e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
@@ -584,7 +594,7 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
             // ---- second epilogue ----
             if (has_z(tile_iter)) {
                 const int cz = (N2 == 128) ? half : 0;
-                const uint32_t slot = n % 3u;
+                const uint32_t slot = n % kSl;
                 uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
                 mbar_wait(&z_full[acc], (tile_iter >> 1) & 1);
                 tc_fence_after_sync();
@@ -687,7 +697,10 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                 mbar_wait(&a_empty[slot], ((it / a.a_stages) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[slot], kATileBytes);
-                    tma_load_3d(&amap, &a_full[slot], sA + slot * kATileBytes, kb * kTileK, 0, px0);
+                    if (a.kb_split > 0 && kb >= a.kb_split)
+                        tma_load_3d(&amap2, &a_full[slot], sA + slot * kATileBytes, (kb - a.kb_split) * kTileK, 0, px0);
+                    else
+                        tma_load_3d(&amap, &a_full[slot], sA + slot * kATileBytes, kb * kTileK, 0, px0);
                 }
                 __syncwarp();
             }

@@ -1527,37 +1527,38 @@ int launch_fuse2_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
 }
 
 // The residual form with eight epilogue warps and in-place residual slabs (conv_fuse2e_kernel).
-int g_fuse2e = getenv("WD_FUSE2E") ? atoi(getenv("WD_FUSE2E")) : 1;
-template <int N2>
+int g_fuse2e = getenv("WD_FUSE2E") ? atoi(getenv("WD_FUSE2E")) : 1;   // 1: residual blocks only, 2: + block 0 (measured neutral: 256.5 vs 258.5 us, that launch is HBM-write-bound at 5.6 TB/s)
+template <int N2, bool RES = true>
 int launch_fuse2e_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int n_clips, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = wd::conv_fuse2e_kernel<N2>;
+    auto kfn = wd::conv_fuse2e_kernel<N2, RES>;
     if (!configured) {
         WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
+    constexpr int kSl = RES ? 3 : 2;   // slabs per epilogue warp
     wd::Fuse2Args p{};
     p.bias1 = c3.bias;
     p.bias2 = c1n.bias;
     p.M = n_clips * c3.Hout * c3.Wout * 8;
     p.num_tiles = (p.M + wd::kTileM - 1) / wd::kTileM;
     p.kblocks = c3.kblocks;
-    p.kb_split = 0;
+    p.kb_split = c3.kb_split;
     p.shift = c1n.fold == 32 ? 1 : 0;
-    // shared memory: A ring | W3 (resident) | W1' (resident) | 8 warps x 3 in-place slabs | barriers
-    const int fixed = p.kblocks * 256 * 128 + N2 * 256 * 2 + 8 * 3 * wd::kEpiSlab + 1024 + 1024;
+    // shared memory: A ring | W3 (resident) | W1' (resident) | 8 warps x kSl in-place slabs | barriers
+    const int fixed = p.kblocks * 256 * 128 + N2 * 256 * 2 + 8 * kSl * wd::kEpiSlab + 1024 + 1024;
     p.a_stages = 4;
     while (p.a_stages > 2 && fixed + p.a_stages * wd::kATileBytes > 232448) --p.a_stages;
     p.off_w1 = p.a_stages * wd::kATileBytes;
     p.off_w2 = p.off_w1 + p.kblocks * 256 * 128;
     p.off_out = p.off_w2 + N2 * 256 * 2;
     p.off_res = p.off_out;
-    p.off_bar = p.off_out + 8 * 3 * wd::kEpiSlab;
+    p.off_bar = p.off_out + 8 * kSl * wd::kEpiSlab;
     const size_t smem = (size_t)p.off_bar + 1024 + 1024;
     if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1 (8 epilogue warps): %zu bytes of shared memory", smem);
     const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
-    WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kF2eThreads, smem, st, c3.wmap, c1n.wmap, c3.amap, c3.omap, c3.rmap,
-                       c1n.omap, p));
+    WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kF2eThreads, smem, st, c3.wmap, c1n.wmap, c3.amap,
+                       c3.kb_split > 0 ? c3.amap32 : c3.amap, c3.omap, RES ? c3.rmap : c3.omap, c1n.omap, p));
     return WD_OK;
 }
 
@@ -1569,6 +1570,10 @@ int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool h
         return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused conv3 + conv1 kernel", c3.name.c_str(), c1n.name.c_str());
     if (has_res && g_fuse2e && c3.kblocks == 1 && c3.kb_split == 0 && (n_clips * c3.Hout * c3.Wout * 8) % wd::kTileM == 0)
         return c1n.Cout == 64 ? launch_fuse2e_t<64>(e, c3, c1n, n_clips, st) : launch_fuse2e_t<128>(e, c3, c1n, n_clips, st);
+    // block 0 (K1 = [y2 | x], no residual): the eight-warp epilogue too (WD_FUSE2E=1 keeps the four-warp kernel for it)
+    if (!has_res && g_fuse2e >= 2 && c3.kblocks == 2 && c3.kb_split == 1 && c1n.Cout == 64 &&
+        (n_clips * c3.Hout * c3.Wout * 8) % wd::kTileM == 0)
+        return launch_fuse2e_t<64, false>(e, c3, c1n, n_clips, st);
     if (c1n.Cout == 64)
         return has_res ? launch_fuse2_t<true, 64>(e, c3, c1n, n_clips, st) : launch_fuse2_t<false, 64>(e, c3, c1n, n_clips, st);
     return has_res ? launch_fuse2_t<true, 128>(e, c3, c1n, n_clips, st) : launch_fuse2_t<false, 128>(e, c3, c1n, n_clips, st);
