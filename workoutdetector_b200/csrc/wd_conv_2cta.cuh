@@ -128,6 +128,9 @@ struct Conv2CtaArgs {
     int prefetch;       // L2-prefetch distance of the A operand in k-blocks (0 = off)
     // TAP variant (A_TAP boxes, 112-row tiles; see wd_conv_v4.cuh): geometry of the convolution
     int Hout, Wout, S, stride, pad, cin_blocks, tiles_w, tap_bh, num_m;  // num_m = ceil(M / 112)
+    int a_split;            // A-producer warps: 0 / 1 = warp 6 alone, 2 = warps 6, 7 take alternate k-blocks, 4 = warps 6, 7, 12, 13
+                            // (512-thread launch)
+    int w_split;            // W-producer warps: 0 / 1 = warp 4 alone, 2 = warps 4 and 14 (512-thread launch)
     int kb_split, stride2;  // TAP: fused stride-2 downsample — k-blocks >= kb_split come from the second A map (`rmap` slot)
 };
 
@@ -136,7 +139,7 @@ struct Conv2CtaArgs {
 //              (tap, channel block) k-block is one or two strided 5-D boxes; a pair computes two consecutive tiles.
 // RES: residual added in place in the slab the TMA load delivered it to (as the 8-warp epilogue of conv_v4_kernel).
 template <int BN, bool TAP, bool RES, int SLABS = 0>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(RES ? 384 : 512, 1)   // warps 12-15 exist only in launches with extra producer warps
 conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_constant__ CUtensorMap amap,
                  const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap16,
                  const __grid_constant__ CUtensorMap rmap, const Conv2CtaArgs a) {
@@ -181,6 +184,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 mbar_init(&tmem_empty_bar[s], 16);
             }
             if (TAP && a.kb_split > 0) tma_prefetch_desc(&rmap);
+            if (TAP) *reinterpret_cast<volatile int*>(bars + 20) = -1;   // A producer's progress (tile iteration), read by the L2 prefetcher
             if (RES) {
                 tma_prefetch_desc(&rmap);
                 for (int s = 0; s < 24; ++s) mbar_init(&bars[192 + s], 1);
@@ -202,7 +206,7 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
     if (warp != 4 && warp != 5) pdl_grid_dependency_wait();
 
-    if (warp < 4 || warp >= 8) {
+    if (warp < 4 || (warp >= 8 && warp < 12)) {
         // ==========================================================================================
         // Epilogue: this CTA's 128 rows x 256 columns, eight warps (with 256 x 256 pair tiles the MMA of a tile is
         // about as long as a four-warp epilogue; two warps per scheduler overlap each other's issue latencies)
@@ -318,16 +322,26 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
         }
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
-    } else if (warp == 4 || warp == 6) {
+    } else if (warp == 4 || warp == 6 || (warp == 7 && a.a_split >= 2) || ((warp == 12 || warp == 13) && a.a_split >= 4) ||
+               (warp == 14 && a.w_split >= 2)) {
         // ==========================================================================================
         // Producers (both CTAs): warp 4 = this CTA's half of W, warp 6 = this CTA's 128 rows of A
         // ==========================================================================================
-        const bool is_w = (warp == 4);
+        const bool is_w = (warp == 4 || warp == 14);
+        // a_split (TAP): warps 6 and 7 issue the A boxes of alternate k-blocks — a strided 5-D box of 112 separate 128-byte
+        // rows keeps one issuing thread busy for longer than the 512 tensor cycles of its k-block
+        const int ways = is_w ? (a.w_split >= 2 ? 2 : 1) : (a.a_split >= 4 ? 4 : (a.a_split >= 2 ? 2 : 1));
+        const int a_sub = is_w ? (warp == 14 ? 1 : 0) : (warp == 6 ? 0 : (warp == 7 ? 1 : warp - 10));
         uint32_t it = 0;
-        Tracer tr{(a.trace && blockIdx.x == 0) ? a.trace + (is_w ? 1 : 2) * 2048 : nullptr, 0};
-        for (int tile = pair; tile < a.num_tiles; tile += npairs) {
+        Tracer tr{(a.trace && blockIdx.x == 0 && (warp == 4 || warp == 6)) ? a.trace + (is_w ? 1 : 2) * 2048 : nullptr, 0};
+        int ptile_iter = 0;
+        for (int tile = pair; tile < a.num_tiles; tile += npairs, ++ptile_iter) {
             const int m_tile = (tile / a.n_tiles) * 2 + (int)rank;
             const int px0 = (m_tile * kTileM) >> 3;
+            if (TAP && warp == 6 && a.prefetch) {
+                if (lane == 0) *reinterpret_cast<volatile int*>(bars + 20) = ptile_iter;
+                __syncwarp();
+            }
             // TAP: the tile is bh image rows of 14 / bh pixels; row j = (clip tn[j], output row toh[j], first pixel tow)
             int tn[2] = {0, 0}, toh[2] = {0, 0}, tow = 0;
             if (TAP) {
@@ -344,12 +358,13 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
             int tap_r = 0, tap_s = 0, cb = 0;
             for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
                 const int slot = it % k2cStages;
+                const bool mine = (int)(it % (uint32_t)ways) == a_sub;
                 tr.mark();
-                mbar_wait(&empty[slot], ((it / k2cStages) & 1) ^ 1);
+                if (mine) mbar_wait(&empty[slot], ((it / k2cStages) & 1) ^ 1);
                 tr.mark();
                 const uint32_t leader_full = mapa_shared(smem_u32(&full[slot]), 0);
                 uint8_t* stage = smem + slot * k2cStage;
-                if (elect_one()) {
+                if (mine && elect_one()) {
                     // the leader announces the bytes of both CTAs for its operand, the peer just arrives
                     if (rank == 0)
                         mbar_arrive_expect_tx_cluster(leader_full, is_w ? BN * kTileK * 2 : 2 * (TAP ? kStripRows * 128 : 16384));
@@ -375,6 +390,50 @@ conv_2cta_kernel(const __grid_constant__ CUtensorMap wmap128, const __grid_const
                 }
                 __syncwarp();
                 if (TAP && ++cb == a.cin_blocks) {  // k-blocks are tap-major: (r, s, channel block)
+                    cb = 0;
+                    if (++tap_s == a.S) {
+                        tap_s = 0;
+                        ++tap_r;
+                    }
+                }
+            }
+        }
+    } else if (TAP && warp == 7 && a.prefetch && a.a_split < 2) {
+        // ==========================================================================================
+        // L2 prefetcher (TAP): while the A producer works on tile i, the boxes of this CTA's tile i + 1 are pulled from
+        // HBM into L2.  The ring holds about one tile of A (84-96 KiB per CTA), too little for the HBM latency of the
+        // strided boxes (profiles/r02_ncu_step_batch64.txt: layer2.0.conv3 at 3.5 TB/s with the tensor pipe 47 % busy);
+        // from L2 the same loads return in half the time.  Paced by the producer's progress word in shared memory.
+        // ==========================================================================================
+        volatile int* progress = reinterpret_cast<volatile int*>(bars + 20);
+        int tile_iter = 0;
+        for (int tile = pair; tile + npairs < a.num_tiles; tile += npairs, ++tile_iter) {
+            while (*progress < tile_iter) __nanosleep(200);
+            const int nt = tile + npairs;
+            const int m_tile = (nt / a.n_tiles) * 2 + (int)rank;
+            int tn[2] = {0, 0}, toh[2] = {0, 0}, tow = 0;
+            for (int j = 0; j < a.tap_bh; ++j) {
+                int q = m_tile * a.tap_bh + j;
+                if (a.tap_bh == 1) {
+                    tow = (q % a.tiles_w) * kStripPixels;
+                    q /= a.tiles_w;
+                }
+                toh[j] = q % a.Hout;
+                tn[j] = q / a.Hout;
+            }
+            int tap_r = 0, tap_s = 0, cb = 0;
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                const bool second = a.kb_split > 0 && kb >= a.kb_split;
+                const CUtensorMap* mp = second ? &rmap : &amap;
+                const int st2 = second ? a.stride2 : a.stride;
+                const int cc = (second ? kb - a.kb_split : cb) * kTileK;
+                if (elect_one()) {
+                    for (int j = 0; j < a.tap_bh; ++j)
+                        tma_prefetch_l2_5d(mp, cc, 0, tow * st2 + (second ? 0 : tap_s - a.pad),
+                                           toh[j] * st2 + (second ? 0 : tap_r - a.pad), tn[j]);
+                }
+                __syncwarp();
+                if (++cb == a.cin_blocks) {
                     cb = 0;
                     if (++tap_s == a.S) {
                         tap_s = 0;
@@ -650,6 +709,8 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         __syncwarp();
     } else if (warp == 4) {
         // ============================== W producer: this CTA's half of every tap ==============================
+        // (a second W-producer warp taking alternate taps was measured neutral on every shape: the 2-D W boxes are not
+        // issue-bound, unlike the strided 5-D A boxes of the tap mode)
         uint32_t it = 0;
         int tile, n0, nc;
         for (int w = pair; work_of(w, tile, n0, nc); w += npairs) {
@@ -725,6 +786,8 @@ conv_2cta_strip_kernel(const __grid_constant__ CUtensorMap wmap_half, const __gr
         }
     } else {
         // ============================== A producers: warp 6 + r loads input row h-1+r ==============================
+        // (MODE 2: splitting a tap row's box between two issuing warps was measured neutral — contiguous 5-D boxes are
+        // not issue-bound, unlike the element-strided boxes of the tap mode)
         const int prow = warp - 6;
         uint32_t it = 0;
         int tile, n0, nc;

@@ -979,7 +979,19 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     p.num_m = (a.M + tile_rows - 1) / tile_rows;
     p.num_tiles = ((p.num_m + 1) / 2) * p.n_tiles;
     p.trace = g_trace;
-    p.prefetch = 0;
+    // TAP: L2 prefetch of the next tile's A boxes by the idle warp 7. WD_2CTA_TAP_PF: 0 = off, 1 = kernels with a fused
+    // stride-2 downsample (conv3 of block 0 in layers 2-4), 2 = every tap-mode launch
+    static const int tap_pf = getenv("WD_2CTA_TAP_PF") ? atoi(getenv("WD_2CTA_TAP_PF")) : 0;
+    p.prefetch = (TAP && (tap_pf >= 2 || (tap_pf == 1 && c.kb_split > 0))) ? 1 : 0;
+    // Extra producer warps of the tap-mode launches (they take k-blocks round-robin).  A strided 5-D A box costs one
+    // issuing thread more than the 512 tensor cycles of its k-block: with four A warps and two W warps (512-thread
+    // launch) conv3 + stride-2 downsample of block 0 in layers 2-4 went 182 -> 148, 166 -> 128, 171 -> 121 us.
+    // The same split was measured neutral for the 1x1 launches (A or W), for the residual kernel (A) and for the W
+    // producers of the strip kernels: their 2-D / 3-D boxes are not issue-bound.  WD_2CTA_ASPLIT = 1 | 2 | 4, WD_2CTA_WSPLIT = 1 | 2.
+    static const int asplit = getenv("WD_2CTA_ASPLIT") ? atoi(getenv("WD_2CTA_ASPLIT")) : 4;
+    static const int wsplit = getenv("WD_2CTA_WSPLIT") ? atoi(getenv("WD_2CTA_WSPLIT")) : 2;
+    p.a_split = (TAP && !RES) ? asplit : 1;
+    p.w_split = (TAP && !RES) ? wsplit : 1;
     p.Hout = a.Hout; p.Wout = a.Wout; p.S = a.S; p.stride = a.stride; p.pad = a.pad; p.cin_blocks = a.cin_blocks;
     p.tiles_w = std::max(1, a.Wout / wd::kStripPixels);
     p.tap_bh = (TAP && a.Wout == 7) ? 2 : 1;
@@ -989,7 +1001,7 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);  // a pair keeps one n-tile (bias)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3((p.a_split >= 4 || p.w_split >= 2) ? 512 : 384);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
