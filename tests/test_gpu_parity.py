@@ -230,6 +230,8 @@ CONV_CASES = [
     (3, 28, 64, 64, 3, 1, 0, 1, 0, "strip", 64),          # two-rows-per-tile kernel (v4): 28 x 28, odd clip count
     (1, 14, 64, 64, 3, 1, 0, 0, 0, "strip", 64),          # ... one strip per row, fewer tiles than SMs, no ReLU
     (28, 28, 64, 64, 1, 1, 8, 1, 0, "gather", 64),        # layer1.0.conv1 as TMA tile + in-smem shift fix-up: 1372 tiles, the 8-slot ring wraps
+    (5, 28, 256, 128, 3, 1, 0, 1, 0, "strip", 128),       # two-output-rows pair kernel (conv_2cta_rows2_kernel): four channel blocks, ReLU
+    (2, 56, 128, 128, 3, 1, 0, 0, 0, "strip", 128),       # ... 56 x 56: two strip pairs per image row
 ]
 
 

@@ -24,6 +24,7 @@
 #include "wd_tdn_kernels.cuh"
 #include "wd_conv_fuse2.cuh"
 #include "wd_conv_fuse3.cuh"
+#include "wd_conv_2cta_rows2.cuh"
 #include "wd_conv_strip2.cuh"
 
 namespace {
@@ -1208,6 +1209,46 @@ int launch_strip2s(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cuda
     return WD_OK;
 }
 
+// 3x3 stride 1 with 128 output channels on CTA pairs, two output rows per tile: N = 256 pair MMAs (wd_conv_2cta_rows2.cuh)
+int g_rows2 = getenv("WD_ROWS2") ? atoi(getenv("WD_ROWS2")) : 1;
+int launch_rows2(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = wd::conv_2cta_rows2_kernel;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    wd::Rows2Args p{};
+    p.bias = a.bias;
+    p.H = a.Hout;
+    p.W = a.Wout;
+    p.cin_blocks = a.cin_blocks;
+    p.relu = a.relu;
+    p.strip_pairs = a.Wout / (2 * wd::kStripPixels);
+    p.num_tiles = (a.M / (a.Hout * a.Wout * 8)) * (a.Hout / 2) * p.strip_pairs;
+    p.off_w = 2 * wd::kR2AStage;
+    p.off_out = p.off_w + wd::kR2WRegion;
+    p.off_bar = p.off_out + 4 * wd::kEpiSlab;
+    const int total = p.off_bar + 2048 + 1024;
+    const int pairs = std::min(p.num_tiles, sm_count / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(wd::kR2Threads);
+    cfg.dynamicSmemBytes = total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    WD_CUDA(cudaLaunchKernelEx(&cfg, kfn, c.wmap_half, c.amap, c.omap, c.omap16, p));
+    return WD_OK;
+}
+
 // 3x3 stride 2, 128 -> 128 (layer2.0.conv2): contiguous input-row boxes, pixel stride 2 in the MMA descriptor
 int launch_strip2d(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool configured = false;
@@ -1237,6 +1278,9 @@ int launch_v4(const ConvLayer& c, wd::ConvArgs a, int sm_count, cudaStream_t st)
     if (g_s2_pair128 && g_2cta >= 3 && c.has_strip7 && c.stride == 2 && c.tile_n == 128 && a.residual == nullptr && a.fold == 0)
         return launch_2cta_strip_mode<2, 128>(c, a, sm_count, st);
     if (g_strip2 >= 3 && c.has_s2 && a.residual == nullptr && c.kb_split == 0) return launch_strip2d(c, a, sm_count, st);
+    if (g_rows2 && g_2cta >= 2 && c.a_mode == wd::A_STRIP && c.tile_n == 128 && c.Cout == 128 && c.Cin % 64 == 0 &&
+        a.residual == nullptr && a.Hout % 2 == 0 && a.Wout % (2 * wd::kStripPixels) == 0 && a.fold == 0)
+        return launch_rows2(c, a, sm_count, st);
     if (g_strip2 >= 2 && c.a_mode == wd::A_STRIP && c.tile_n == 128 && c.Cout == 128 && a.residual == nullptr &&
         a.Hout % 2 == 0 && a.Wout % wd::kStripPixels == 0 && a.fold == 0)
         return launch_strip2s(c, a, sm_count, st);
