@@ -497,8 +497,7 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
         // free once the store of position r - 3 has been read; at the end of unit n (store n committed, wait_group.read 1
         // done) that holds for every r <= n + 2.
         auto request_upto = [&](uint32_t limit) {
-            if (!RES) return;
-            while ((int)req_ti < my_tiles && req_n <= limit) {
+            while (RES && (int)req_ti < my_tiles && req_n <= limit) {
                 const int t2 = (int)blockIdx.x + (int)req_ti * (int)gridDim.x;
                 const uint32_t slot = req_n % 3u;
                 if (elect_one()) {
