@@ -172,9 +172,11 @@ int wd_infer_host_sync(wd_engine* e);
 
 /* ---- introspection, tuning and test hooks (not part of the reference surface) ---- */
 int wd_engine_num_ops(const wd_engine* e);
-/* info[0..9] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head, 4 fused stem conv + maxpool, 5 blend with up-sampled
+/* info[0..11] = kind (0 stem conv, 1 conv, 2 maxpool, 3 head, 4 fused stem conv + maxpool, 5 blend with up-sampled
  *              tensor (TDN), 6 motion excitation + temporal Conv1d (TDN)), Cin, Cout, ksize, stride, Hout, Wout, fold,
- *              a_mode (0 gather, 1 stem, 2 tma, 3 strip, -1 n/a), tile_n;   macs_per_clip = multiply-accumulates per clip */
+ *              a_mode (0 gather, 1 stem, 2 tma, 3 strip, -1 n/a), tile_n, out_sub (2: the op stores its output at the even
+ *              (h, w) pixels only, as a compact [Hout/2, Wout/2] tensor — nothing but the next layer's stride-2 downsample
+ *              reads it; 1 otherwise), reserved;   macs_per_clip = multiply-accumulates per clip.  info must hold 12 ints. */
 int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int32_t* info, double* macs_per_clip);
 /* After op `idx` runs in the next forwards, its output is converted to fp32 NCHW frames [n_clips*8, C, H, W]
  * at dst (device).  idx < 0 disables.  The head op (logits) cannot be tapped.  idx + 65536 taps the SECOND output of a

@@ -282,6 +282,8 @@ def _run_taps(engine, frames, n_clips, taps_ref, tol):
         engine.forward(frames)
         torch.cuda.synchronize()
         ref = taps_ref[op["name"]]
+        if op.get("out_sub", 1) == 2:   # the last block output of layers 1 / 2 is stored at its even pixels only
+            ref = ref[:, :, ::2, ::2]
         err = float((t.cpu() - ref).abs().max()) / (float(ref.abs().max()) + 1e-6)
         if err > worst[1]:
             worst = (op["name"], err)

@@ -367,7 +367,11 @@ def test_fused_layer2_conv3_conv1_equals_unfused(weights, n_clips):
         e.close()
     for key in ("11", "10"):
         for nm, t in taps[key].items():
-            assert torch.equal(t, taps["01"][nm]), (key, nm, float((t - taps["01"][nm]).abs().max()))
+            ref = taps["01"][nm]
+            if ref.shape != t.shape:   # fused plan: layer 2's output is stored at its even pixels only (Op out_sub = 2)
+                assert nm == "layer2.3.conv3" and t.shape[2] * 2 == ref.shape[2]
+                ref = ref[:, :, ::2, ::2]
+            assert torch.equal(t, ref), (key, nm, float((t - ref).abs().max()))
         assert torch.equal(out[key], out["01"]), key
 
 

@@ -69,6 +69,8 @@ struct Fuse2Args {
     int res_depth;        // residual slabs in flight per epilogue warp (2 or 3)
     int shift;            // 1: the second convolution sees TemporalShift(y) with fold 32 (TSM); 0: y itself (TDN layer 1)
     int off_w1, off_w2, off_out, off_res, off_bar;   // byte offsets; the A ring starts at 0
+    int sub, H, W;        // conv_fuse2e_kernel: sub = 1 -> y is stored at the even (h, w) pixels only, through `smap`, as a
+                          // compact [clips, H/2, W/2, 8, 256] tensor (W % 4 == 0: a warp's four pixels share an image row)
 };
 
 template <bool HAS_RES, int N2>
@@ -415,6 +417,7 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                    const __grid_constant__ CUtensorMap omap,    // y  [rows, 256], box {64, 32}
                    const __grid_constant__ CUtensorMap rmap,    // residual, same geometry
                    const __grid_constant__ CUtensorMap zmap,    // z  [rows, N2],  box {64, 32}
+                   const __grid_constant__ CUtensorMap smap,    // compact y [rows / 4, 256], box {64, 8} (a.sub)
                    const Fuse2Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -518,6 +521,12 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
         int tile_iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const int mrow = tile * kTileM + quarter * 32;
+            // subsampled store: this warp's four pixels (w .. w+3 of image row h); only even rows / columns are kept
+            int sub_row = -1;
+            if (a.sub) {
+                const int px = mrow >> 3, w = px % a.W, q = px / a.W, h = q % a.H, n = q / a.H;
+                if ((h & 1) == 0) sub_row = (((n * (a.H >> 1) + (h >> 1)) * (a.W >> 1)) + (w >> 1)) * 8;
+            }
             const int acc = tile_iter & 1;
             const uint32_t tacc = lane_base + acc * 256;
             mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
@@ -566,7 +575,12 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
-                    tma_store_2d(&omap, my_slab + slot * kEpiSlab, c * 64, mrow);
+                    if (!a.sub) {
+                        tma_store_2d(&omap, my_slab + slot * kEpiSlab, c * 64, mrow);
+                    } else if (sub_row >= 0) {   // pixels w and w + 2: slab rows 0..7 and 16..23
+                        tma_store_2d(&smap, my_slab + slot * kEpiSlab, c * 64, sub_row);
+                        tma_store_2d(&smap, my_slab + slot * kEpiSlab + 2048, c * 64, sub_row + 8);
+                    }
                     tma_store_commit();
                 }
                 __syncwarp();

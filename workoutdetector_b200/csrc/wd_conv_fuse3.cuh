@@ -46,6 +46,8 @@ struct Fuse3Args {
     int safe_order;       // 1: M1(g+2) is issued only after M2(g) has COMPLETED (y_free barrier) instead of relying on the
                           // in-order execution of tcgen05.mma for the write-after-read on chunk g's TMEM columns
     int off_w, off_out, off_bar;   // byte offsets; the A slots (2 x 32 KiB) start at 0
+    int sub, H, W;        // sub = 1: y is stored at the even (h, w) pixels only, through `smap`, as a compact
+                          // [clips, H/2, W/2, 8, N1] tensor (W % 4 == 0: a warp's four pixels share an image row)
 };
 
 template <int N2>
@@ -56,6 +58,7 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                   const __grid_constant__ CUtensorMap omap,    // y  [rows, N1],  box {64, 32}
                   const __grid_constant__ CUtensorMap rmap,    // residual, same geometry
                   const __grid_constant__ CUtensorMap zmap,    // z  [rows, N2],  box {64, 32}
+                  const __grid_constant__ CUtensorMap smap,    // compact y [rows / 4, N1], box {64, 8} (a.sub)
                   const Fuse3Args a) {
     static_assert(N2 == 128 || N2 == 256, "next conv1 has 128 or 256 output channels");
     constexpr int kStagesPerM2 = N2 / 128;   // ring stages one M2 consumes (one per k-block when N2 = 256)
@@ -162,6 +165,12 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
         int tile_iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const int mrow = tile * kTileM + quarter * 32;
+            // subsampled store: this warp's four pixels (w .. w+3 of image row h); only even rows / columns are kept
+            int sub_row = -1;
+            if (a.sub) {
+                const int px = mrow >> 3, w = px % a.W, q = px / a.W, h = q % a.H, nn = q / a.H;
+                if ((h & 1) == 0) sub_row = (((nn * (a.H >> 1) + (h >> 1)) * (a.W >> 1)) + (w >> 1)) * 8;
+            }
 #pragma unroll 1
             for (int j = 0; j < n_chunks; ++j, ++g, ++n) {
                 const uint32_t buf = g & 1u;
@@ -204,7 +213,12 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
-                    tma_store_2d(&omap, my_slab + slot * kEpiSlab, col0, mrow);
+                    if (!a.sub) {
+                        tma_store_2d(&omap, my_slab + slot * kEpiSlab, col0, mrow);
+                    } else if (sub_row >= 0) {   // pixels w and w + 2: slab rows 0..7 and 16..23
+                        tma_store_2d(&smap, my_slab + slot * kEpiSlab, col0, sub_row);
+                        tma_store_2d(&smap, my_slab + slot * kEpiSlab + 2048, col0, sub_row + 8);
+                    }
                     tma_store_commit();
                 }
                 __syncwarp();

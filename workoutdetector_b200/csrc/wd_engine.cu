@@ -167,6 +167,8 @@ struct ConvLayer {
     CUtensorMap amap32;  // fold 32: 32-channel SWIZZLE_64B boxes of the {C, T, P} view (k-block 0 = two halves)
     CUtensorMap amap_s2; // stride-2 3x3 (conv_strip2d_kernel): contiguous 16-pixel row boxes of the INPUT {C, T, W, H, clips}
     CUtensorMap omap24;  // output, box {64, 24}
+    CUtensorMap omap_sub;  // compact [rows / 4, Cout] view of the output buffer, box {64, 8} (one pixel): Op::out_sub == 2
+    bool ds_in_sub = false;  // the fused stride-2 downsample reads a compact (already subsampled) tensor: pixel stride 1
     CUtensorMap amap9;   // 7 x 7 strip mode: {C, T, W, H, clips} view, box {64, 8, 9, 1, 1}
     bool has_strip7 = false;   // 3x3 stride-1 convolution on 7 x 7 images: conv_2cta_strip_kernel<256, true>
     bool has_s2 = false;
@@ -190,6 +192,10 @@ struct Op {
     int in2_buf = -1;        // fused downsample: the block input (second A source)
     int conv2 = -1;          // layer 1: conv1 of the NEXT block, computed by the same kernel (wd_conv_fuse2.cuh)
     int out2_buf = -1;       // ... and the buffer its output goes to
+    int out_sub = 1;         // 2: the main output is stored at the even (h, w) pixels only, as a compact [H/2, W/2] tensor — the
+                             // last block of layers 1 / 2, whose output is read by nothing but the next layer's stride-2
+                             // downsample (the next conv1 runs inside the same kernel)
+    int in2_sub = 1;         // 2: the fused downsample's source (in2_buf) is such a compact tensor: stride 1 instead of 2
     std::string name;
     int C = 0, H = 0, W = 0;  // output dims per frame
     int Hy = 0;               // OP_BLEND: resolution of the up-sampled operand
@@ -211,6 +217,7 @@ struct wd_engine {
     int fuse2_requested = 1;    // WD_FUSE2 at create time
     int fuse3 = 1;              // layer-2 conv3 + next conv1 in one kernel (wd_conv_fuse3.cuh); WD_FUSE3 at create time
     int fuse3_requested = 1;
+    int sub_out = 1;            // WD_SUB_OUT at create time: subsampled store of the last block output of layers 1 / 2 (TSM plan)
     int fuse3_safe = 1;         // WD_FUSE3_SAFE at create time: explicit barrier between M2(g) and M1(g+2) (wd_conv_fuse3.cuh)
     int use_2cta = 4;          // per-engine copies of the launch-helper switches (set_option "use_2cta" / "pdl" /
     int pdl = 1;               // "prefetch_kblocks"); run_forward installs them before launching
@@ -323,6 +330,10 @@ int build_plan(wd_engine* e) {
     int H = e->convs[ci].Hout / 2;
     int inplanes = 64;
     int pre_c1 = -1, pre_buf = -1;  // conv1 of the coming block already scheduled inside the previous conv3 kernel
+    bool cur_sub = false;           // `cur` holds the previous layer's output at its even (h, w) pixels only (Op::out_sub)
+    const int fuse2e_env = getenv("WD_FUSE2E") ? atoi(getenv("WD_FUSE2E")) : 1;
+    // the subsampled store needs the eight-warp fused kernels and the fused stride-2 downsample in the next layer
+    const bool sub_ok = e->sub_out && e->desc.mode == WD_MODE_BF16 && e->fuse_ds >= 2 && fuse2e_env >= 1;
     for (int L = 0; L < 4; ++L) {
         for (int b = 0; b < blocks[L]; ++b) {
             const int stride = (L > 0 && b == 0) ? 2 : 1;
@@ -349,10 +360,13 @@ int build_plan(wd_engine* e) {
                 o1 = fr[2];
             }
             const int fold = e->desc.is_shift ? inplanes / e->desc.shift_div : 0;
+            const bool in_sub = cur_sub;   // this block's input buffer holds the even pixels only
+            cur_sub = false;
             int c1;
             if (pre_c1 >= 0) {
                 c1 = pre_c1;   // created (and scheduled) with the previous block's conv3
             } else {
+                if (in_sub) return fail(WD_ERR_INVALID, "%s: conv1 cannot read a subsampled block output", nm.c_str());
                 c1 = add_conv(nm + ".conv1", pre + ".conv1.net.weight", pre + ".conv1.weight", pre + ".bn1", inplanes,
                               width, 1, 1, H, fold, 1);
                 add_conv_op(c1, cur, b1, -1);
@@ -363,6 +377,8 @@ int build_plan(wd_engine* e) {
             add_conv_op(c2, b1, o0, -1);
             const int Ho = e->convs[c2].Hout;
             int idbuf = cur;
+            if (in_sub && !(b == 0 && e->desc.mode == WD_MODE_BF16 && (stride == 1 ? e->fuse_ds >= 1 : e->fuse_ds >= 2)))
+                return fail(WD_ERR_INVALID, "%s: the identity path cannot read a subsampled block output", nm.c_str());
             // Block 0 of layer 1 (stride 1): out = relu(W3*y2 + b3 + Wd*x + bd) is ONE GEMM over the concatenated
             // K = [y2 | x] with weights [W3 | Wd] and bias b3 + bd — the 1.6 MB/frame downsample output is never written
             // or read back as a residual (bf16 mode; FP32_VALIDATE keeps the reference's op sequence).
@@ -374,6 +390,7 @@ int build_plan(wd_engine* e) {
                 if (fuse) {
                     e->convs[cd].fused_away = true;
                 } else {
+                    if (in_sub) return fail(WD_ERR_INVALID, "%s: an un-fused downsample cannot read a subsampled block output", nm.c_str());
                     add_conv_op(cd, cur, o1, -1);
                     idbuf = o1;
                 }
@@ -385,6 +402,7 @@ int build_plan(wd_engine* e) {
                 e->convs[c3].fuse_stride = stride;
                 add_conv_op(c3, o0, b1, -1);
                 e->ops.back().in2_buf = cur;
+                e->ops.back().in2_sub = in_sub ? 2 : 1;
                 e->ops.back().macs_per_clip += 8.0 * Ho * Ho * (double)outp * inplanes;
             } else {
                 add_conv_op(c3, o0, b1, idbuf);  // conv1's buffer is free again
@@ -404,6 +422,10 @@ int build_plan(wd_engine* e) {
                 o3.conv2 = pre_c1;
                 o3.out2_buf = o1;
                 o3.macs_per_clip += 8.0 * Ho * Ho * (double)e->convs[pre_c1].Cout * outp;
+                if (last && sub_ok && b > 0 && Ho % 2 == 0 && Ho % 4 == 0) {   // layer 1's output: only layer2.0's downsample reads it
+                    o3.out_sub = 2;
+                    cur_sub = true;
+                }
             }
             // Layer 2, blocks with an identity residual: the same fusion with streamed weights and a chunked output tile
             // (wd_conv_fuse3.cuh).  The next conv1 is 512 -> 128 inside layer 2 and layer3.0.conv1 (512 -> 256, still
@@ -421,6 +443,10 @@ int build_plan(wd_engine* e) {
                 o3.conv2 = pre_c1;
                 o3.out2_buf = o1;
                 o3.macs_per_clip += 8.0 * Ho * Ho * (double)e->convs[pre_c1].Cout * outp;
+                if (last && sub_ok && Ho % 4 == 0) {   // layer 2's output: only layer3.0's downsample reads it
+                    o3.out_sub = 2;
+                    cur_sub = true;
+                }
             }
             cur = b1;
             H = Ho;
@@ -904,7 +930,7 @@ int launch_v4_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaStr
     p.tiles_w = (AMODE == wd::A_STRIP || AMODE == wd::A_TAP) ? std::max(1, a.Wout / wd::kStripPixels) : 1;
     p.tap_bh = (AMODE == wd::A_TAP && a.Wout == 7) ? 2 : 1;
     p.kb_split = c.kb_split;
-    p.stride2 = c.fuse_ds >= 0 ? c.fuse_stride : 1;
+    p.stride2 = (c.fuse_ds >= 0 && !c.ds_in_sub) ? c.fuse_stride : 1;
     // L2 prefetch of the A operand only where the smem ring cannot cover HBM latency: few stages, several k-blocks per tile
     p.prefetch_kblocks = (g_prefetch_kblocks >= 0) ? g_prefetch_kblocks : ((sp.a_stages <= 3 && a.kblocks >= 4) ? 4 : 0);
     p.trace = g_trace;
@@ -997,7 +1023,7 @@ int launch_2cta_t(const ConvLayer& c, const wd::ConvArgs& a, int sm_count, cudaS
     p.tiles_w = std::max(1, a.Wout / wd::kStripPixels);
     p.tap_bh = (TAP && a.Wout == 7) ? 2 : 1;
     p.kb_split = c.kb_split;
-    p.stride2 = c.fuse_ds >= 0 ? c.fuse_stride : 1;
+    p.stride2 = (c.fuse_ds >= 0 && !c.ds_in_sub) ? c.fuse_stride : 1;
     int pairs = std::min(p.num_tiles, sm_count / 2);
     pairs = std::max(p.n_tiles, (pairs / p.n_tiles) * p.n_tiles);  // a pair keeps one n-tile (bias)
     cudaLaunchConfig_t cfg{};
@@ -1585,7 +1611,7 @@ int launch_fuse2_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int 
 // The residual form with eight epilogue warps and in-place residual slabs (conv_fuse2e_kernel).
 int g_fuse2e = getenv("WD_FUSE2E") ? atoi(getenv("WD_FUSE2E")) : 1;   // 1: residual blocks only, 2: + block 0 (measured neutral: 256.5 vs 258.5 us, that launch is HBM-write-bound at 5.6 TB/s)
 template <int N2, bool RES = true>
-int launch_fuse2e_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int n_clips, cudaStream_t st) {
+int launch_fuse2e_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int n_clips, cudaStream_t st, bool sub = false) {
     static bool configured = false;
     auto kfn = wd::conv_fuse2e_kernel<N2, RES>;
     if (!configured) {
@@ -1613,19 +1639,26 @@ int launch_fuse2e_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int
     const size_t smem = (size_t)p.off_bar + 1024 + 1024;
     if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1 (8 epilogue warps): %zu bytes of shared memory", smem);
     const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
+    p.sub = sub ? 1 : 0;
+    p.H = c3.Hout;
+    p.W = c3.Wout;
+    if (sub && (c3.Wout % 4 != 0 || c3.Hout % 2 != 0)) return fail(WD_ERR_INVALID, "%s: subsampled store needs W %% 4 == 0", c3.name.c_str());
     WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kF2eThreads, smem, st, c3.wmap, c1n.wmap, c3.amap,
-                       c3.kb_split > 0 ? c3.amap32 : c3.amap, c3.omap, RES ? c3.rmap : c3.omap, c1n.omap, p));
+                       c3.kb_split > 0 ? c3.amap32 : c3.amap, c3.omap, RES ? c3.rmap : c3.omap, c1n.omap,
+                       sub ? c3.omap_sub : c3.omap, p));
     return WD_OK;
 }
 
 // Layer 1: conv3 of a block + conv1 of the next block in one kernel (wd_conv_fuse2.cuh).  c3's maps (W, A, second A
 // source, output, residual) are the ones load_weights built for the plain kernel; c1n contributes W, bias and the z map.
-int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool has_res, int n_clips, cudaStream_t st) {
+int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool has_res, int n_clips, cudaStream_t st,
+                 bool sub = false) {
     if (c3.tile_n != 256 || c3.Cout != 256 || (c1n.Cout != 64 && c1n.Cout != 128) || c1n.tile_n != c1n.Cout ||
         c1n.Cin != 256 || (c1n.fold != 32 && c1n.fold != 0) || c3.a_mode != wd::A_TMA || c3.kblocks < 1 || c3.kblocks > 2)
         return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused conv3 + conv1 kernel", c3.name.c_str(), c1n.name.c_str());
     if (has_res && g_fuse2e && c3.kblocks == 1 && c3.kb_split == 0 && (n_clips * c3.Hout * c3.Wout * 8) % wd::kTileM == 0)
-        return c1n.Cout == 64 ? launch_fuse2e_t<64>(e, c3, c1n, n_clips, st) : launch_fuse2e_t<128>(e, c3, c1n, n_clips, st);
+        return c1n.Cout == 64 ? launch_fuse2e_t<64>(e, c3, c1n, n_clips, st, sub) : launch_fuse2e_t<128>(e, c3, c1n, n_clips, st, sub);
+    if (sub) return fail(WD_ERR_INVALID, "%s: the subsampled store exists in the eight-warp fused kernel only", c3.name.c_str());
     // block 0 (K1 = [y2 | x], no residual): the eight-warp epilogue too (WD_FUSE2E=1 keeps the four-warp kernel for it)
     if (!has_res && g_fuse2e >= 2 && c3.kblocks == 2 && c3.kb_split == 1 && c1n.Cout == 64 &&
         (n_clips * c3.Hout * c3.Wout * 8) % wd::kTileM == 0)
@@ -1637,7 +1670,8 @@ int launch_fuse2(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, bool h
 
 // Layer 2: conv3 (+ identity residual) of a block + conv1 of the next block in one kernel (wd_conv_fuse3.cuh).
 template <int N2>
-int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, const void* res, int n_clips, cudaStream_t st) {
+int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, const void* res, int n_clips, cudaStream_t st,
+                   bool sub) {
     static bool configured = false;
     auto kfn = wd::conv_fuse3_kernel<N2>;
     if (!configured) {
@@ -1669,19 +1703,25 @@ int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, cons
     const size_t smem = (size_t)p.off_bar + 1024 + 1024;
     if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1 (layer 2): %zu bytes of shared memory", smem);
     const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
+    p.sub = sub ? 1 : 0;
+    p.H = c3.Hout;
+    p.W = c3.Wout;
+    if (sub && (c3.Wout % 4 != 0 || c3.Hout % 2 != 0)) return fail(WD_ERR_INVALID, "%s: subsampled store needs W %% 4 == 0", c3.name.c_str());
     WD_CUDA(launch_pdl(kfn, grid, (unsigned)wd::kF3Threads, smem, st, c3.wmap_half, c1n.wmap, c3.amap, c3.omap, c3.rmap,
-                       c1n.omap, p));
+                       c1n.omap, sub ? c3.omap_sub : c3.omap, p));
     return WD_OK;
 }
 
-int launch_fuse3(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, const void* res, int n_clips, cudaStream_t st) {
+int launch_fuse3(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, const void* res, int n_clips, cudaStream_t st,
+                 bool sub = false) {
     const bool has_res = res != nullptr;
     if (!has_res || c3.tile_n != 256 || c3.Cout % 256 != 0 || c3.Cin != 128 || c3.kblocks != 2 || c3.kb_split != 0 ||
         c3.a_mode != wd::A_TMA || c1n.Cin != c3.Cout || (c1n.Cout != 128 && c1n.Cout != 256) || c1n.tile_n != c1n.Cout ||
         (c1n.fold != 64 && c1n.fold != 0) || c3.Cout != 512)
         return fail(WD_ERR_INVALID, "%s + %s: shapes outside the fused layer-2 conv3 + conv1 kernel", c3.name.c_str(),
                     c1n.name.c_str());
-    return c1n.Cout == 128 ? launch_fuse3_t<128>(e, c3, c1n, res, n_clips, st) : launch_fuse3_t<256>(e, c3, c1n, res, n_clips, st);
+    return c1n.Cout == 128 ? launch_fuse3_t<128>(e, c3, c1n, res, n_clips, st, sub)
+                           : launch_fuse3_t<256>(e, c3, c1n, res, n_clips, st, sub);
 }
 
 // Motion excitation + temporal Conv1d of one BottleneckShift: four launches (wd_tdn_kernels.cuh).
@@ -1769,9 +1809,9 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
                 wd::conv_f32_kernel<<<grid, 256, 0, st>>>(a);
                 WD_CUDA(cudaGetLastError());
             } else if (o.conv2 >= 0 && c.Cout == 512) {
-                WD_TRY(launch_fuse3(e, c, e->convs[o.conv2], res, n_clips, st));
+                WD_TRY(launch_fuse3(e, c, e->convs[o.conv2], res, n_clips, st, o.out_sub == 2));
             } else if (o.conv2 >= 0) {
-                WD_TRY(launch_fuse2(e, c, e->convs[o.conv2], res != nullptr, n_clips, st));
+                WD_TRY(launch_fuse2(e, c, e->convs[o.conv2], res != nullptr, n_clips, st, o.out_sub == 2));
             } else if (o.in_buf == kInDiff && c.a_mode == wd::A_TAP) {
                 ConvLayer cc = c;  // tap boxes over the caller's difference tensor: its address is known only now
                 WD_TRY(make_amap_tap(&cc.amap, in, c.Cin, c.Win, c.Hin, (size_t)n_clips, 1, wd::kStripPixels));
@@ -1860,17 +1900,18 @@ int run_forward(wd_engine* e, const void* frames, int n_clips, float* logits, fl
             WD_CUDA(cudaGetLastError());
         }
         if ((int)oi == e->tap_idx && e->tap_dst && o.kind != OP_HEAD) {
-            const size_t total = (size_t)n_clips * 8 * o.C * o.H * o.W;
+            const int tH = o.H / o.out_sub, tW = o.W / o.out_sub;   // a subsampled output is captured as stored: [H/2, W/2]
+            const size_t total = (size_t)n_clips * 8 * o.C * tH * tW;
             if ((int64_t)total > e->tap_cap)
                 return fail(WD_ERR_INVALID, "tap buffer too small: need %zu elements, have %lld", total,
                             (long long)e->tap_cap);
             const unsigned grid = (unsigned)((total + 255) / 256);
             if (f32)
                 wd::untile_to_nchw_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(out), e->tap_dst,
-                                                                        n_clips, o.H, o.W, o.C);
+                                                                        n_clips, tH, tW, o.C);
             else
                 wd::untile_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-                    static_cast<const __nv_bfloat16*>(out), e->tap_dst, n_clips, o.H, o.W, o.C);
+                    static_cast<const __nv_bfloat16*>(out), e->tap_dst, n_clips, tH, tW, o.C);
             WD_CUDA(cudaGetLastError());
         }
         if (op_ms) WD_CUDA(cudaEventRecord(ev[oi + 1], st));
@@ -2009,6 +2050,7 @@ int wd_engine_create(const wd_model_desc* d, wd_engine** out) {
     e->fuse3_requested = getenv("WD_FUSE3") ? atoi(getenv("WD_FUSE3")) : 1;
     e->fuse3 = e->fuse3_requested;   // TSM layer 2 (shift fold 64) and TDN layer 2 (no shift in conv1)
     e->fuse3_safe = getenv("WD_FUSE3_SAFE") ? atoi(getenv("WD_FUSE3_SAFE")) : 1;
+    e->sub_out = getenv("WD_SUB_OUT") ? atoi(getenv("WD_SUB_OUT")) : 1;
     int r = d->arch == WD_ARCH_TDN_R50 ? build_plan_tdn(e) : build_plan(e);
     if (r != WD_OK) {
         delete e;
@@ -2218,6 +2260,8 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
             if (o.res_buf >= 0) WD_TRY(make_omap(&c.rmap, e->buf[o.res_buf], c.Cout, rows));
             if (o.conv2 >= 0)   // the next block's conv1 output, written by the same kernel
                 WD_TRY(make_omap(&e->convs[o.conv2].omap, e->buf[o.out2_buf], e->convs[o.conv2].Cout, rows));
+            if (o.out_sub == 2)  // compact [H/2, W/2] view of the same buffer, one pixel (8 rows) per box
+                WD_TRY(make_omap(&c.omap_sub, e->buf[o.out_buf], c.Cout, rows / 4, 8));
             if (c.a_mode == wd::A_STRIP) {
                 WD_TRY(make_omap(&c.omap16, e->buf[o.out_buf], c.Cout, rows, 16));
                 WD_TRY(make_amap5(&c.amap, e->buf[o.in_buf], c.Cin, c.Win, c.Hin, (size_t)e->desc.max_clips));
@@ -2252,6 +2296,11 @@ int wd_engine_load_weights(wd_engine* e, const wd_named_tensor* t, int n) {
                 }
                 if (o.in2_buf >= 0) {  // fused stride-2 downsample: the block input at twice the resolution
                     const ConvLayer& d = e->convs[c.fuse_ds];
+                    c.ds_in_sub = o.in2_sub == 2;
+                    if (c.ds_in_sub)   // the block input was stored at its even pixels only: a stride-1 view of [H/2, W/2]
+                        WD_TRY(make_amap_tap(&c.amap32, e->buf[o.in2_buf], d.Cin, d.Win / 2, d.Hin / 2,
+                                             (size_t)e->desc.max_clips, 1, c.Wout == 7 ? 7 : wd::kStripPixels));
+                    else
                     WD_TRY(make_amap_tap(&c.amap32, e->buf[o.in2_buf], d.Cin, d.Win, d.Hin, (size_t)e->desc.max_clips,
                                          d.stride, c.Wout == 7 ? 7 : wd::kStripPixels));
                     c.rmap = c.amap32;  // the CTA-pair kernel takes the second A map in its (unused) residual slot
@@ -2642,7 +2691,8 @@ int wd_engine_op_info(const wd_engine* e, int idx, char* name, int name_cap, int
     const Op& o = e->ops[idx];
     if (name && name_cap > 0) snprintf(name, name_cap, "%s", o.name.c_str());
     if (info) {
-        for (int i = 0; i < 10; ++i) info[i] = 0;
+        for (int i = 0; i < 12; ++i) info[i] = 0;
+        info[10] = o.out_sub;
         info[0] = o.kind;
         info[2] = o.C;
         info[5] = o.H;

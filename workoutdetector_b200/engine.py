@@ -94,13 +94,13 @@ class Engine:
     def ops(self) -> List[dict]:
         out = []
         name = C.create_string_buffer(64)
-        info = (C.c_int32 * 10)()
+        info = (C.c_int32 * 12)()
         macs = C.c_double()
         for i in range(self.lib.wd_engine_num_ops(self.h)):
             check(self.lib.wd_engine_op_info(self.h, i, name, 64, info, C.byref(macs)))
             out.append(dict(index=i, name=name.value.decode(), kind=OP_KINDS[info[0]], cin=info[1], cout=info[2],
                             k=info[3], stride=info[4], hout=info[5], wout=info[6], fold=info[7],
-                            a_mode=A_MODES[info[8]], tile_n=info[9], macs_per_clip=macs.value))
+                            a_mode=A_MODES[info[8]], tile_n=info[9], out_sub=max(1, info[10]), macs_per_clip=macs.value))
         return out
 
     def set_tap(self, idx: int, n_clips: int = 1, second_cout: int = 0) -> Optional[torch.Tensor]:
@@ -112,7 +112,9 @@ class Engine:
             self._tap = None
             return None
         o = self.ops()[idx]
-        t = torch.empty((n_clips * 8, second_cout or o["cout"], o["hout"], o["wout"]), dtype=torch.float32, device=self.device)
+        sub = 1 if second_cout else o["out_sub"]   # a subsampled output is captured as stored: [H/2, W/2]
+        t = torch.empty((n_clips * 8, second_cout or o["cout"], o["hout"] // sub, o["wout"] // sub), dtype=torch.float32,
+                        device=self.device)
         check(self.lib.wd_engine_set_tap(self.h, idx + (65536 if second_cout else 0), _ptr(t), t.numel()))
         self._tap = t
         return t
