@@ -69,6 +69,7 @@ struct Fuse2Args {
     int res_depth;        // residual slabs in flight per epilogue warp (2 or 3)
     int shift;            // 1: the second convolution sees TemporalShift(y) with fold 32 (TSM); 0: y itself (TDN layer 1)
     int off_w1, off_w2, off_out, off_res, off_bar;   // byte offsets; the A ring starts at 0
+    int defer_z;          // conv_fuse2e_kernel: the second epilogue of tile i runs after the first epilogue of tile i + 1
     int sub, H, W;        // conv_fuse2e_kernel: sub = 1 -> y is stored at the even (h, w) pixels only, through `smap`, as a
                           // compact [clips, H/2, W/2, 8, 256] tensor (W % 4 == 0: a warp's four pixels share an image row)
 };
@@ -510,12 +511,55 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                 }
                 __syncwarp();
                 ++req_n;
-                if (++req_i == 2) {     // the tile's z unit (if this warp runs it) takes a ring position too
-                    req_i = 0;
-                    if (has_z((int)req_ti)) ++req_n;
+                if (++req_i == 2) {     // a z unit (if this warp runs it) takes a ring position too: the tile's own, or,
+                    req_i = 0;          // with defer_z, the PREVIOUS tile's (it runs after this tile's y units)
+                    if (a.defer_z ? (req_ti > 0 && has_z((int)req_ti - 1)) : has_z((int)req_ti)) ++req_n;
                     ++req_ti;
                 }
             }
+        };
+        auto z_unit = [&](int ti) {
+            const int ztile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int mrow = ztile * kTileM + quarter * 32;
+            const int acc = ti & 1;
+            const uint32_t tacc = lane_base + acc * 256;
+            const int cz = (N2 == 128) ? half : 0;
+            const uint32_t slot = n % kSl;
+            uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
+            mbar_wait(&z_full[acc], (ti >> 1) & 1);
+            tc_fence_after_sync();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tacc + 128 + cz * 64, v0);
+            tmem_ld32(tacc + 128 + cz * 64 + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
+            __syncwarp();
+            const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
+                const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
+                const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                    __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                    __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                    __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+                *reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+                tma_store_2d(&zmap, my_slab + slot * kEpiSlab, cz * 64, mrow);
+                tma_store_commit();
+                tma_store_wait_read1();
+            }
+            __syncwarp();
+            request_upto(n + 2);
+            ++n;
         };
         request_upto(2);
         int tile_iter = 0;
@@ -524,8 +568,8 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
             // subsampled store: this warp's four pixels (w .. w+3 of image row h); only even rows / columns are kept
             int sub_row = -1;
             if (a.sub) {
-                const int px = mrow >> 3, w = px % a.W, q = px / a.W, h = q % a.H, n = q / a.H;
-                if ((h & 1) == 0) sub_row = (((n * (a.H >> 1) + (h >> 1)) * (a.W >> 1)) + (w >> 1)) * 8;
+                const int px = mrow >> 3, w = px % a.W, q = px / a.W, h = q % a.H, nn = q / a.H;
+                if ((h & 1) == 0) sub_row = (((nn * (a.H >> 1) + (h >> 1)) * (a.W >> 1)) + (w >> 1)) * 8;
             }
             const int acc = tile_iter & 1;
             const uint32_t tacc = lane_base + acc * 256;
@@ -605,46 +649,15 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
             if (elect_one()) mbar_arrive(&y_full[acc]);
             __syncwarp();
             // ---- second epilogue ----
-            if (has_z(tile_iter)) {
-                const int cz = (N2 == 128) ? half : 0;
-                const uint32_t slot = n % kSl;
-                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
-                mbar_wait(&z_full[acc], (tile_iter >> 1) & 1);
-                tc_fence_after_sync();
-                uint32_t v0[32], v1[32];
-                tmem_ld32(tacc + 128 + cz * 64, v0);
-                tmem_ld32(tacc + 128 + cz * 64 + 32, v1);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (elect_one()) mbar_arrive(&tmem_empty_bar[acc]);
-                __syncwarp();
-                const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
-                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
-                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
-                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
-                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
-                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
-                    *reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (elect_one()) {
-                    tma_store_2d(&zmap, my_slab + slot * kEpiSlab, cz * 64, mrow);
-                    tma_store_commit();
-                    tma_store_wait_read1();
-                }
-                __syncwarp();
-                request_upto(n + 2);
-                ++n;
+            // defer_z: the z unit of tile i runs AFTER the y units of tile i + 1 — the second GEMM of tile i (issued once all
+            // eight warps have handed over their y chunks) then executes under those y units instead of under a stall
+            if (!a.defer_z) {
+                if (has_z(tile_iter)) z_unit(tile_iter);
+            } else if (tile_iter > 0 && has_z(tile_iter - 1)) {
+                z_unit(tile_iter - 1);
             }
         }
+        if (a.defer_z && tile_iter > 0 && has_z(tile_iter - 1)) z_unit(tile_iter - 1);
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
     } else if (warp == 8) {

@@ -46,6 +46,8 @@ struct Fuse3Args {
     int safe_order;       // 1: M1(g+2) is issued only after M2(g) has COMPLETED (y_free barrier) instead of relying on the
                           // in-order execution of tcgen05.mma for the write-after-read on chunk g's TMEM columns
     int off_w, off_out, off_bar;   // byte offsets; the A slots (2 x 32 KiB) start at 0
+    int defer_z;          // 1: the second epilogue of tile i runs after the FIRST chunk of tile i + 1, so the last M2 of
+                          // tile i (it completes the second accumulator) executes under that chunk instead of under a stall
     int sub, H, W;        // sub = 1: y is stored at the even (h, w) pixels only, through `smap`, as a compact
                           // [clips, H/2, W/2, 8, N1] tensor (W % 4 == 0: a warp's four pixels share an image row)
 };
@@ -147,9 +149,17 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
         // request the residual slab of unit n (if it is a first-epilogue unit) into slab n % 3
         auto request = [&](uint32_t n) {
             if (n >= total_units) return;
-            const uint32_t r = n % (uint32_t)upt;
+            uint32_t r = n % (uint32_t)upt, ti2 = n / (uint32_t)upt;
+            if (a.defer_z && n >= (uint32_t)n_chunks) {
+                // unit order: tile 0 = y0 .. y(last); every later tile = y0, z units of the previous tile, y1 .. y(last)
+                const uint32_t m = n - (uint32_t)n_chunks, rr = m % (uint32_t)upt;
+                ti2 = 1u + m / (uint32_t)upt;
+                if ((int)ti2 >= my_tiles) return;              // the last tile's z units
+                if (rr >= 1u && rr <= (uint32_t)kE2Units) return;   // second-epilogue unit: no residual
+                r = rr == 0u ? 0u : rr - (uint32_t)kE2Units;
+            }
             if (r >= (uint32_t)n_chunks) return;               // second-epilogue unit: no residual
-            const int t2 = (int)blockIdx.x + (int)(n / (uint32_t)upt) * (int)gridDim.x;
+            const int t2 = (int)blockIdx.x + (int)ti2 * (int)gridDim.x;
             const uint32_t slot = n % 3u;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&my_res_bar[slot], kEpiSlab);
@@ -158,10 +168,55 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
             }
             __syncwarp();
         };
-        request(0);
-        request(1);
         uint32_t n = 0, g = 0;
         uint32_t res_uses[3] = {0, 0, 0};                      // completed residual loads per slot (barrier parity)
+        // ---- second epilogue of tile iteration ti: z = relu(acc2 + b1'); this warp's units are cz = half, half + 2, ... ----
+        auto z_units = [&](int ti) {
+            const int mrow = ((int)blockIdx.x + ti * (int)gridDim.x) * kTileM + quarter * 32;
+            mbar_wait(acc2_full, ti & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int ez = 0; ez < kE2Units; ++ez, ++n) {
+                const int cz = half + 2 * ez;
+                const uint32_t slot = n % 3u;
+                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(lane_base + 256 + cz * 64, v0);
+                tmem_ld32(lane_base + 256 + cz * 64 + 32, v1);
+                tmem_ld_wait();
+                if (ez == kE2Units - 1) {   // this warp's part of the second accumulator is drained
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(acc2_empty);
+                    __syncwarp();
+                }
+                const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
+                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
+                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
+                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+                    *reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&zmap, my_slab + slot * kEpiSlab, cz * 64, mrow);
+                    tma_store_commit();
+                    tma_store_wait_read1();
+                }
+                __syncwarp();
+                request(n + 2);
+            }
+        };
+        request(0);
+        request(1);
         int tile_iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const int mrow = tile * kTileM + quarter * 32;
@@ -244,50 +299,15 @@ conv_fuse3_kernel(const __grid_constant__ CUtensorMap w1map,   // W3  [N1, 128],
                 }
                 __syncwarp();
                 request(n + 2);                 // ... which is the slab of unit n + 2
+                if (a.defer_z && j == 0 && tile_iter > 0) {   // the previous tile's second epilogue (its ring positions follow)
+                    ++n;
+                    z_units(tile_iter - 1);
+                    --n;                         // the loop header advances n past this chunk's unit
+                }
             }
-            // ---- second epilogue: z = relu(acc2 + b1'); this warp's units are cz = half, half + 2, ... ----
-            mbar_wait(acc2_full, tile_iter & 1);
-            tc_fence_after_sync();
-#pragma unroll 1
-            for (int ez = 0; ez < kE2Units; ++ez, ++n) {
-                const int cz = half + 2 * ez;
-                const uint32_t slot = n % 3u;
-                uint8_t* slab = my_slab + slot * kEpiSlab + row_off;
-                uint32_t v0[32], v1[32];
-                tmem_ld32(lane_base + 256 + cz * 64, v0);
-                tmem_ld32(lane_base + 256 + cz * 64 + 32, v1);
-                tmem_ld_wait();
-                if (ez == kE2Units - 1) {   // this warp's part of the second accumulator is drained
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (elect_one()) mbar_arrive(acc2_empty);
-                    __syncwarp();
-                }
-                const float4* bsrc = reinterpret_cast<const float4*>(a.bias2 + cz * 64);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
-                    const float4 b0 = __ldg(bsrc + 2 * q), b1 = __ldg(bsrc + 2 * q + 1);
-                    const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
-                                        __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w,
-                                        __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
-                                        __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
-                    *reinterpret_cast<uint4*>(slab + ((q ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (elect_one()) {
-                    tma_store_2d(&zmap, my_slab + slot * kEpiSlab, cz * 64, mrow);
-                    tma_store_commit();
-                    tma_store_wait_read1();
-                }
-                __syncwarp();
-                request(n + 2);
-            }
+            if (!a.defer_z) z_units(tile_iter);
         }
+        if (a.defer_z && tile_iter > 0) z_units(tile_iter - 1);
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
     } else if (warp == 8) {

@@ -1639,6 +1639,8 @@ int launch_fuse2e_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, int
     const size_t smem = (size_t)p.off_bar + 1024 + 1024;
     if (smem > 232448) return fail(WD_ERR_INVALID, "fused conv3 + conv1 (8 epilogue warps): %zu bytes of shared memory", smem);
     const unsigned grid = (unsigned)std::min(p.num_tiles, e->sm_count);
+    static const int defer_z = getenv("WD_F2E_DEFER_Z") ? atoi(getenv("WD_F2E_DEFER_Z")) : 1;
+    p.defer_z = defer_z;
     p.sub = sub ? 1 : 0;
     p.H = c3.Hout;
     p.W = c3.Wout;
@@ -1687,6 +1689,8 @@ int launch_fuse3_t(wd_engine* e, const ConvLayer& c3, const ConvLayer& c1n, cons
     p.n_chunks = c3.Cout / wd::kF3Chunk;
     p.shift = c1n.fold == 64 ? 1 : 0;
     p.safe_order = e->fuse3_safe;
+    static const int f3_defer_z = getenv("WD_F3_DEFER_Z") ? atoi(getenv("WD_F3_DEFER_Z")) : 1;
+    p.defer_z = f3_defer_z;
     // Two measured dead ends, kept as switches: WD_F3_RES_PREFETCH=1 (one 128 KiB bulk L2 prefetch of the next tile's
     // residual per tile: 195 -> 232 us, the prefetch competes with the demand loads) and WD_F3_ASLOTS=1 (one A slot, three
     // W stages: 185 -> 196 us for N2 = 128, 251 -> 248 us for N2 = 256: the W ring is not what starves the kernel).
