@@ -399,9 +399,9 @@ conv_fuse2_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], box
 // i.e. on columns the OTHER warp of the quarter reads in its first unit — the two warps meet on a named barrier (one per
 // quarter) right after their first tcgen05.ld, before either writes anything back.
 // Second epilogue: N2 / 64 units per quarter; with N2 = 64 the two warps of a quarter alternate tiles.
-// Warp roles (352 threads): 0-7 epilogue, 8 W producer, 9 MMA issuer, 10 A producer.
+// Warp roles (320 threads): 0-7 epilogue, 8 W (once) + A producer, 9 MMA issuer.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kF2eThreads = 352;
+constexpr int kF2eThreads = 320;   // ten warps: 200 registers per thread (eleven warps round up to 384 threads: 168, with spills)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -594,6 +594,13 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                 if (i == 0) named_bar_sync(1 + quarter, 64);
                 uint32_t pk[32];
                 const float4* bsrc = reinterpret_cast<const float4*>(a.bias1 + c * 64);
+                // all eight residual cells of the row first: the stores below go to the same slab, so a load cannot be
+                // hoisted over them and every cell would pay its LDS latency in turn (profiles/r02s5_ncu_hot_fuse2e128.txt)
+                uint4 rqs[8];
+                if (RES) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) rqs[q] = *reinterpret_cast<const uint4*>(slab + ((q ^ sw) << 4));
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint32_t* v = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
@@ -604,7 +611,7 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
                                   __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
                                   __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
                     if (RES) {
-                        const uint4 rq = *cell;
+                        const uint4 rq = rqs[q];
                         const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -660,13 +667,6 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
         if (a.defer_z && tile_iter > 0 && has_z(tile_iter - 1)) z_unit(tile_iter - 1);
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
-    } else if (warp == 8) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(w_bar, (uint32_t)a.kblocks * kF2N1 * kTileK * 2 + N2 * kF2K2 * 2);
-            for (int kb = 0; kb < a.kblocks; ++kb) tma_load_2d(&w1map, w_bar, sW1 + kb * kF2N1 * kTileK * 2, kb * kTileK, 0);
-            for (int kb = 0; kb < kF2K2 / kTileK; ++kb) tma_load_2d(&w2map, w_bar, sW2 + kb * N2 * kTileK * 2, kb * kTileK, 0);
-        }
-        __syncwarp();
     } else if (warp == 9) {
         constexpr uint32_t idesc1 = umma_idesc_bf16(kTileM, kF2N1);
         constexpr uint32_t idesc2 = umma_idesc_bf16(kTileM, N2);
@@ -715,6 +715,14 @@ conv_fuse2e_kernel(const __grid_constant__ CUtensorMap w1map,   // [256, K1], bo
         }
         if (tile_iter > 0) second(tile_iter - 1);
     } else {
+        // warp 8: both weight sets once (they do not depend on the previous kernel), then the A tiles
+        if (elect_one()) {
+            mbar_arrive_expect_tx(w_bar, (uint32_t)a.kblocks * kF2N1 * kTileK * 2 + N2 * kF2K2 * 2);
+            for (int kb = 0; kb < a.kblocks; ++kb) tma_load_2d(&w1map, w_bar, sW1 + kb * kF2N1 * kTileK * 2, kb * kTileK, 0);
+            for (int kb = 0; kb < kF2K2 / kTileK; ++kb) tma_load_2d(&w2map, w_bar, sW2 + kb * N2 * kTileK * 2, kb * kTileK, 0);
+        }
+        __syncwarp();
+        pdl_grid_dependency_wait();
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int px0 = (tile * kTileM) >> 3;
